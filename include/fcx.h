@@ -1,0 +1,126 @@
+/*
+ * fcx.h -- C ABI of the B200-native drop-in for the "-c lz77" path of my_compress.cpp.
+ *
+ * Every entry point below replaces one reference interface ("mc:N" = line N of
+ * /root/reference/my_compress.cpp, \n-based).  Plain pointers and sizes only; errors are
+ * negative return codes (the reference exit(-1)s on allocation failure, mc:73-93, and
+ * returns 0 on NULL arguments, mc:2122-2123 -- a library must not do either silently).
+ * All compute runs in hand-written sm_100a CUDA kernels; there is no CPU fallback: without
+ * a CUDA device every compute call returns FCX_ERR_NO_DEVICE.
+ *
+ * Output is byte-identical to the reference: FCX7 container (mc:101-109, 4073-4136) of
+ * independent 1 MiB blocks, each "u32 size | payload" with the payload of mc:2115-2253.
+ */
+#ifndef FCX_H
+#define FCX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCX_BLOCK_BYTES (1u << 20) /* mc:113 BLOCK_BYTES */
+#define FCX_HEADER_BYTES 10u       /* mc:101-109 stCmpFileHead, #pragma pack(1) */
+
+enum {
+    FCX_OK = 0,
+    FCX_ERR_ARG = -1,       /* NULL pointer / bad size / misaligned device pointer */
+    FCX_ERR_NO_DEVICE = -2, /* no CUDA device, or the kernels could not be loaded */
+    FCX_ERR_CUDA = -3,      /* a CUDA runtime call failed; see fcx_last_error() */
+    FCX_ERR_CAPACITY = -4,  /* output buffer smaller than the compressed result */
+    FCX_ERR_FORMAT = -5,    /* not an FCX7 stream / corrupt payload (mc:4146-4152) */
+    FCX_ERR_UNSUPPORTED = -6 /* e.g. FCX8 (lz78) containers: not on this path */
+};
+
+/* Thread-local description of the last error on the calling thread ("" if none). */
+const char *fcx_last_error(void);
+
+/* Number of CUDA devices visible (0 when none; never an error). */
+int fcx_device_count(void);
+
+/* Worst-case container size for n input bytes (the reference's caller uses a fixed 2 MiB
+ * per-block buffer, mc:4088; this is the tight version of that convention). */
+uint64_t fcx_compress_bound(uint64_t n);
+
+/* ---- host-buffer entry points (H2D/D2H inside) ------------------------------------ */
+
+/* Replaces my_compress_file_lz77(void *pData, uInt32 totalBytes, uInt8 *pOut) (mc:2115,
+ * called at mc:4099): one block (n <= 1 MiB) -> payload bytes, written to out, count in
+ * *out_n.  Does not print (the reference printf()s per block, mc:2249). */
+int fcx_compress_block_lz77(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t out_cap, uint32_t *out_n);
+
+/* Replaces the compress branch of main() (mc:4073-4136): whole buffer -> FCX7 container,
+ * header included (u32 byte count and u16 block count wrap exactly like the reference).
+ * device_mask: bit g set = use CUDA device g; 0 = device 0.  Blocks are sharded over the
+ * devices in contiguous ranges; no data-path collective (blocks share no state). */
+int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_n,
+                      uint32_t device_mask);
+
+/* Replaces my_decompress_file_lz77 (mc:2255, called at mc:4182) for one payload, and the
+ * decompress branch of main() (mc:4138-4202) for a container.  Output is what the
+ * reference's decoder produces, including its single-symbol-stream behaviour. */
+int fcx_decompress_block_lz77(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap,
+                              uint32_t *out_n);
+int fcx_decompress_lz77(const uint8_t *file, uint64_t nbytes, uint8_t *out, uint64_t out_cap, uint64_t *out_n,
+                        uint32_t device_mask);
+
+/* ---- device-resident entry points (what the throughput metric times) --------------- */
+
+typedef struct fcx_ctx fcx_ctx;
+
+/* Workspace for batches of up to max_batch_blocks 1 MiB blocks on CUDA device `device`
+ * (about 6.7 MiB of HBM per block).  stream: a cudaStream_t (0 = legacy default). */
+int fcx_ctx_create(fcx_ctx **ctx, int device, uint32_t max_batch_blocks);
+void fcx_ctx_destroy(fcx_ctx *ctx);
+int fcx_ctx_set_stream(fcx_ctx *ctx, void *cuda_stream);
+
+/* Compress n bytes resident at d_in (16-byte aligned device pointer) into d_out
+ * (16-byte aligned, out_cap bytes, >= fcx_compress_bound(n) is always enough).
+ * flags & FCX_WITH_HEADER: emit the 10-byte file header first, describing
+ * (total_bytes_for_header, total_blocks_for_header) -- a rank compressing one shard of a
+ * larger file passes the whole file's figures on shard 0 and no header elsewhere.
+ * Asynchronous on the context's stream; fcx_ctx_finish() synchronises and reports. */
+#define FCX_WITH_HEADER 1u
+int fcx_compress_lz77_device(fcx_ctx *ctx, const uint8_t *d_in, uint64_t n, uint8_t *d_out, uint64_t out_cap,
+                             uint32_t flags, uint64_t total_bytes_for_header, uint32_t total_blocks_for_header);
+/* Waits for the stream; *out_n = bytes written by the last fcx_compress_lz77_device call. */
+int fcx_ctx_finish(fcx_ctx *ctx, uint64_t *out_n);
+
+/* Kernel launches issued on this context since creation (bench.py's gpu_launches). */
+uint64_t fcx_ctx_launch_count(const fcx_ctx *ctx);
+
+/* Per-stage device figures of the last compress call, for the roofline report:
+ * s_in  = bytes fed to the Huffman encode kernel (all four streams of all blocks),
+ * s_out = bytes of code words it wrote, tokens / matches = LZ77 totals. */
+typedef struct {
+    uint64_t s_in, s_out, tokens, matches, container_bytes, blocks;
+} fcx_stats;
+int fcx_ctx_stats(fcx_ctx *ctx, fcx_stats *st);
+
+/* Per-kernel timing hooks: when enabled, each stage of the next compress calls is
+ * bracketed by CUDA events on the context's stream.  ms[i] accumulates per stage,
+ * names[i] are static strings; returns the number of stages. */
+int fcx_ctx_enable_timing(fcx_ctx *ctx, int on);
+int fcx_ctx_stage_times(fcx_ctx *ctx, const char **names, float *ms, int cap);
+
+/* ---- stage-level probes (device pointers; used by tests/ to localise parity) -------- */
+
+/* per-position longest match of one block (mc:1446-1514): len[i] in {0,3..257}, dist[i]. */
+int fcx_probe_match(fcx_ctx *ctx, const uint8_t *d_in, uint32_t n, uint16_t *d_len, uint16_t *d_dist);
+/* greedy parse + stream split of one block (mc:1675-1714, 2073-2113, 2150-2161, 1292-1313,
+ * 258-304): host outputs.  streams: bitmap bytes, c bytes, packed-p bytes, Golomb bytes. */
+int fcx_probe_streams(fcx_ctx *ctx, const uint8_t *d_in, uint32_t n, uint32_t *T, uint32_t *Pc, uint32_t *G,
+                      uint8_t *bitmap, uint8_t *c, uint8_t *ppack, uint8_t *golomb);
+/* one Huffman section (mc:987-1104) of S device-resident bytes -> host bytes. */
+int fcx_probe_huffman_section(fcx_ctx *ctx, const uint8_t *d_src, uint32_t S, uint8_t *out, uint32_t out_cap,
+                              uint32_t *out_n);
+
+/* Corpus generator following RandM() of the reference's generator program
+ * (随机数的生成.cpp:26-42) with time() pinned to `seed`: byte i = perm[i] & 0xFF. */
+void fcx_datagen_randm(uint8_t *out, uint32_t m, uint32_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,248 @@
+"""Python face of the C-ABI library (include/fcx.h), mirroring the reference's interface.
+
+Names follow my_compress.cpp: ``my_compress_file_lz77`` (mc:2115) / ``my_decompress_file_lz77``
+(mc:2255) work on one 1 MiB block payload; ``compress`` / ``decompress`` are the two branches
+of ``main`` (mc:4073-4136, mc:4138-4202) on whole buffers.  Everything runs in the CUDA
+kernels of ``libfcx.so``; there is no CPU path and nothing here touches ``oracle/``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libfcx.so")
+_lib = None
+
+BLOCK_BYTES = 1 << 20
+FCX_WITH_HEADER = 1
+
+_u8p = C.POINTER(C.c_uint8)
+
+
+class FcxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fcx error %d: %s" % (code, msg))
+        self.code = code
+
+
+class FcxStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("s_in", "s_out", "tokens", "matches", "container_bytes", "blocks")]
+
+
+EXPORTS = [
+    "fcx_last_error", "fcx_device_count", "fcx_compress_bound", "fcx_compress_block_lz77", "fcx_compress_lz77",
+    "fcx_decompress_block_lz77", "fcx_decompress_lz77", "fcx_ctx_create", "fcx_ctx_destroy", "fcx_ctx_set_stream",
+    "fcx_compress_lz77_device", "fcx_ctx_finish", "fcx_ctx_launch_count", "fcx_ctx_stats", "fcx_ctx_enable_timing",
+    "fcx_ctx_stage_times", "fcx_probe_match", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
+]
+
+
+def lib():
+    """Loads libfcx.so (built in-tree by my_compress_b200/build.py); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise FcxError(-2, "libfcx.so is not built: run `python -m my_compress_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(_LIB_PATH)
+    L.fcx_last_error.restype = C.c_char_p
+    L.fcx_device_count.restype = C.c_int
+    L.fcx_compress_bound.restype = C.c_uint64
+    L.fcx_compress_bound.argtypes = [C.c_uint64]
+    L.fcx_compress_block_lz77.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.fcx_compress_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.fcx_decompress_block_lz77.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.fcx_decompress_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.fcx_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32]
+    L.fcx_ctx_destroy.argtypes = [C.c_void_p]
+    L.fcx_ctx_destroy.restype = None
+    L.fcx_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.fcx_compress_lz77_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32,
+                                           C.c_uint64, C.c_uint32]
+    L.fcx_ctx_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.fcx_ctx_launch_count.argtypes = [C.c_void_p]
+    L.fcx_ctx_launch_count.restype = C.c_uint64
+    L.fcx_ctx_stats.argtypes = [C.c_void_p, C.POINTER(FcxStats)]
+    L.fcx_ctx_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    L.fcx_ctx_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.fcx_probe_match.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.fcx_probe_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fcx_probe_huffman_section.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                            C.POINTER(C.c_uint32)]
+    L.fcx_datagen_randm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.fcx_datagen_randm.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise FcxError(rc, lib().fcx_last_error().decode("utf-8", "replace"))
+
+
+def _host_u8(buf):
+    a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def device_count():
+    return int(lib().fcx_device_count())
+
+
+def compress_bound(n):
+    return int(lib().fcx_compress_bound(int(n)))
+
+
+def device_mask(n_gpus):
+    return (1 << int(n_gpus)) - 1
+
+
+# ---- host-buffer API: what a user of the reference calls ---------------------------------
+
+def my_compress_file_lz77(data):
+    """One block (<= 1 MiB) -> payload bytes; same bytes as mc:2115 writes to pOut."""
+    x = _host_u8(data)
+    out = np.empty(compress_bound(len(x)), np.uint8)
+    n = C.c_uint32(0)
+    _check(lib().fcx_compress_block_lz77(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def my_decompress_file_lz77(payload):
+    """One block payload -> the bytes mc:2255 writes to its FILE*."""
+    x = _host_u8(payload)
+    out = np.empty(BLOCK_BYTES + 8, np.uint8)
+    n = C.c_uint32(0)
+    _check(lib().fcx_decompress_block_lz77(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def compress_into(src, dst, n_gpus=1):
+    """Whole buffer -> FCX7 container written into ``dst`` (numpy uint8, ideally pinned); returns byte count."""
+    n = C.c_uint64(0)
+    _check(lib().fcx_compress_lz77(src.ctypes.data, src.size, dst.ctypes.data, dst.size, C.byref(n), device_mask(n_gpus)))
+    return int(n.value)
+
+
+def compress(data, n_gpus=1):
+    """``./my_compress -i in -o out -c lz77`` on a buffer: FCX7 container bytes."""
+    x = _host_u8(data)
+    out = np.empty(compress_bound(len(x)), np.uint8)
+    src = x if len(x) else np.zeros(1, np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_compress_lz77(src.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+def decompress(blob, n_gpus=1):
+    """``./my_compress -i in -o out`` on a buffer: what the reference's decoder writes."""
+    x = _host_u8(blob)
+    if len(x) < 10:
+        raise FcxError(-5, "shorter than the 10-byte header")
+    nb = int.from_bytes(x[8:10].tobytes(), "little")
+    out = np.empty(max(1, nb) * (BLOCK_BYTES + 8), np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_decompress_lz77(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+def datagen_randm(m, seed):
+    out = np.empty(m, np.uint8)
+    lib().fcx_datagen_randm(out.ctypes.data, m, seed)
+    return out
+
+
+# ---- device-resident API (torch tensors own the memory; kernels are ours) -----------------
+
+class DeviceCompressor:
+    """Compresses ``torch.uint8`` CUDA tensors in place in HBM on the current torch stream."""
+
+    def __init__(self, device=0, max_batch_blocks=1024):
+        import torch
+
+        self.torch = torch
+        self.device = int(device)
+        self._ctx = C.c_void_p(None)
+        _check(lib().fcx_ctx_create(C.byref(self._ctx), self.device, int(max_batch_blocks)))
+        self.use_stream(torch.cuda.current_stream(self.device))
+
+    def use_stream(self, stream):
+        _check(lib().fcx_ctx_set_stream(self._ctx, C.c_void_p(stream.cuda_stream)))
+
+    def close(self):
+        if self._ctx:
+            lib().fcx_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress_async(self, d_in, d_out, with_header=True, header_bytes=None, header_blocks=None, n=None):
+        n = int(d_in.numel() if n is None else n)
+        hb = n if header_bytes is None else int(header_bytes)
+        hk = (n + BLOCK_BYTES - 1) // BLOCK_BYTES if header_blocks is None else int(header_blocks)
+        _check(lib().fcx_compress_lz77_device(self._ctx, C.c_void_p(d_in.data_ptr()), n, C.c_void_p(d_out.data_ptr()),
+                                              int(d_out.numel()), FCX_WITH_HEADER if with_header else 0, hb, hk & 0xFFFFFFFF))
+
+    def finish(self):
+        n = C.c_uint64(0)
+        _check(lib().fcx_ctx_finish(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    def compress(self, d_in, d_out=None, **kw):
+        if d_out is None:
+            d_out = self.torch.empty(compress_bound(d_in.numel()), dtype=self.torch.uint8, device=d_in.device)
+        self.compress_async(d_in, d_out, **kw)
+        return d_out, self.finish()
+
+    def launch_count(self):
+        return int(lib().fcx_ctx_launch_count(self._ctx))
+
+    def stats(self):
+        s = FcxStats()
+        _check(lib().fcx_ctx_stats(self._ctx, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in FcxStats._fields_}
+
+    def enable_timing(self, on=True):
+        _check(lib().fcx_ctx_enable_timing(self._ctx, 1 if on else 0))
+
+    def stage_times(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        k = lib().fcx_ctx_stage_times(self._ctx, names, ms, 16)
+        return {names[i].decode(): float(ms[i]) for i in range(k)}
+
+    # ---- stage probes (tests) --------------------------------------------------------------
+    def probe_match(self, d_in):
+        t = self.torch
+        n = d_in.numel()
+        ln = t.empty(n, dtype=t.int16, device=d_in.device)
+        ds = t.empty(n, dtype=t.int16, device=d_in.device)
+        _check(lib().fcx_probe_match(self._ctx, C.c_void_p(d_in.data_ptr()), n, C.c_void_p(ln.data_ptr()), C.c_void_p(ds.data_ptr())))
+        return (ln.cpu().numpy().view(np.uint16).astype(np.uint32), ds.cpu().numpy().view(np.uint16).astype(np.uint32))
+
+    def probe_streams(self, d_in):
+        n = d_in.numel()
+        T, Pc, G = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        bm = np.zeros(n // 8 + 64, np.uint8)
+        cs = np.zeros(n + 64, np.uint8)
+        pp = np.zeros(11 * (n // 4 + 1) // 8 + 64, np.uint8)
+        gb = np.zeros(n // 8 + 1024, np.uint8)
+        _check(lib().fcx_probe_streams(self._ctx, C.c_void_p(d_in.data_ptr()), n, C.byref(T), C.byref(Pc), C.byref(G),
+                                       bm.ctypes.data, cs.ctypes.data, pp.ctypes.data, gb.ctypes.data))
+        T, Pc, G = T.value, Pc.value, G.value
+        return {"T": T, "Pc": Pc, "G": G, "bitmap": bm[: (T + 7) // 8].tobytes(), "c": cs[:T].tobytes(),
+                "p": pp[: (11 * Pc) // 8 + 1].tobytes(), "golomb": gb[: 4 * G].tobytes()}
+
+    def probe_huffman_section(self, d_src):
+        S = d_src.numel()
+        out = np.zeros(S + S // 4 + 4096, np.uint8)
+        n = C.c_uint32(0)
+        ptr = d_src.data_ptr() if S else self.torch.zeros(16, dtype=self.torch.uint8, device="cuda:%d" % self.device).data_ptr()
+        _check(lib().fcx_probe_huffman_section(self._ctx, C.c_void_p(ptr), S, out.ctypes.data, len(out), C.byref(n)))
+        return out[: n.value].tobytes()

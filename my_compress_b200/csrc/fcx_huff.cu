@@ -1,0 +1,585 @@
+// fcx_huff.cu -- byte-Huffman section encoder (subsystem 3 of the north star) and the
+// block / container assembler (subsystem 4).
+//
+// Replaces my_huffman_encode_char (mc:987-1104) = histogram (mc:997-1000) +
+// create_huffman_tree (mc:535-617, stable merge sort mc:458-498) + tree serialisation
+// (mc:1021-1066) + huffman_encode_char (mc:849-928), called four times per block by
+// my_compress_file_lz77 (mc:2145,2178,2207,2238), and the payload/container layout of
+// mc:2137-2243 and mc:4078-4129.
+//
+// The tree is NOT canonical: bits are the root->leaf path of the reference's own two-queue
+// construction (merged node goes after equal weights, mc:588; first popped = left = 0), so
+// k_tree replays that construction exactly, one warp per stream.
+//
+// Bit offsets come from scans, never from a serial bit loop: the histogram pass keeps one
+// 256-bin histogram per 8192-symbol chunk, so once code lengths exist the bit length of every
+// chunk is a 256-term dot product; a scan over chunks/sections/blocks then gives every chunk
+// its absolute bit position in the final container, and k_encode writes code words straight
+// into the container (the sections sit at odd byte offsets, so everything is addressed as one
+// little-endian bit stream over the 4-byte aligned output buffer).
+#include "fcx_dev.cuh"
+
+namespace fcx {
+
+// =========================================================================================
+// chunk planning
+// =========================================================================================
+__global__ void __launch_bounds__(1024)
+k_plan(Ws ws, uint32_t nBlocks)
+{
+    __shared__ uint32_t warpSum[32];
+    __shared__ uint32_t running;
+    const uint32_t nSeg = nBlocks * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nSeg; base += 1024) {
+        const uint32_t s = base + tid;
+        uint32_t S = 0, nch = 0, raw = 0;
+        if (s < nSeg) {
+            const uint32_t b = s >> 2, k = s & 3;
+            S = ws.meta[(size_t)b * M_WORDS + M_S0 + k];
+            raw = (k == 0 && S <= 1) ? 1u : 0u;              // mc:2095-2107: bitmap of <= 1 byte stays raw
+            nch = raw ? 0u : (S + kChunkSyms - 1) / kChunkSyms;
+        }
+        uint32_t inc = nch;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warpSum[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+        for (int w = 0; w < 32; w++) { uint32_t v = warpSum[w]; if (w < warp) wbase += v; total += v; }
+        const uint32_t first = running + wbase + inc - nch;
+        if (s < nSeg) {
+            uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+            si[SI_S] = S; si[SI_FIRST_CHUNK] = first; si[SI_NCHUNKS] = nch; si[SI_RAW] = raw;
+            si[SI_R] = 0; si[SI_HDR] = 0; si[SI_W] = 0; si[SI_MAXLEN] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) ws.totals[TOT_CHUNKS] = running;
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_chunks(Ws ws, uint32_t nSeg)
+{
+    const uint32_t s = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nSeg) return;
+    const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+    const uint32_t first = si[SI_FIRST_CHUNK], nch = si[SI_NCHUNKS];
+    for (uint32_t c = lane; c < nch; c += 32) ws.chunkSeg[first + c] = s;
+}
+
+// =========================================================================================
+// histogram: warp-privatised shared-memory bins, one 256-bin histogram kept per chunk
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+k_hist(Ws ws)
+{
+    __shared__ uint32_t wh[8][256];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t nChunks = ws.totals[TOT_CHUNKS];
+    for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+        const uint32_t s = ws.chunkSeg[chunk];
+        const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+        const uint32_t b = s >> 2, k = s & 3;
+        const uint32_t c = chunk - si[SI_FIRST_CHUNK];
+        const uint32_t S = si[SI_S];
+        const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
+        const uint8_t *src = ws.strm[k] + (size_t)b * ws.strmStride[k] + (size_t)c * kChunkSyms;
+        for (int j = tid; j < 8 * 256; j += 256) (&wh[0][0])[j] = 0;
+        __syncthreads();
+        uint32_t *h = wh[warp];
+        for (uint32_t v = tid; v * 16 < cnt; v += 256) {
+            uint4 q = reinterpret_cast<const uint4 *>(src)[v];
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t valid = min(16u, cnt - v * 16);
+            uint32_t cur = w[0] & 0xFF, run = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 16; j++) {
+                uint32_t sym = (w[j >> 2] >> ((j & 3) * 8)) & 0xFF;
+                if (j < valid) {
+                    if (sym == cur) run++;
+                    else { atomicAdd(&h[cur], run); cur = sym; run = 1; }
+                }
+            }
+            if (run) atomicAdd(&h[cur], run);
+        }
+        __syncthreads();
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) sum += wh[w][tid];
+        ws.chunkHist[(size_t)chunk * 256 + tid] = (uint16_t)sum;
+        if (sum) atomicAdd(&ws.segHist[(size_t)s * 256 + tid], sum);
+        __syncthreads();
+    }
+}
+
+// =========================================================================================
+// tree + code table + serialised header, one warp per stream
+// =========================================================================================
+constexpr int TREE_WARPS = 4;
+
+struct TreeSmem {
+    uint32_t key[256];
+    uint32_t sw[256];      // sorted leaf weights
+    uint32_t iw[256];      // internal node weights
+    uint32_t icode[256];   // code prefix of internal nodes
+    uint32_t tab[256];     // code | 1<<len per symbol
+    uint16_t child[512];   // [2j],[2j+1]: tree index (leaf: symbol, internal: 512-R+j')
+    uint8_t ssym[256];     // sorted leaf symbols
+    uint8_t ilen[256];
+    uint8_t hdr[kSegHdrStride];
+};
+
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+k_tree(Ws ws, uint32_t nSeg)
+{
+    __shared__ TreeSmem smAll[TREE_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t s = blockIdx.x * TREE_WARPS + warp;
+    if (s >= nSeg) return;
+    TreeSmem &sm = smAll[warp];
+    uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+    const uint32_t S = si[SI_S];
+    if (S == 0 || si[SI_RAW]) return;                       // mc:989-990: empty stream emits nothing
+
+    // ---- stable sort of the non-zero weights: unique key = weight<<8 | symbol ------------
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int sym = lane + 32 * i;
+        w[i] = ws.segHist[(size_t)s * 256 + sym];
+        sm.key[sym] = w[i] ? ((w[i] << 8) | (uint32_t)sym) : 0xFFFFFFFFu;
+        sm.tab[sym] = 0;
+    }
+    __syncwarp();
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (w[i]) {
+            const uint32_t mine = sm.key[lane + 32 * i];
+            uint32_t rank = 0;
+            for (int m = 0; m < 256; m++) rank += (sm.key[m] < mine) ? 1u : 0u;
+            sm.ssym[rank] = (uint8_t)(lane + 32 * i);
+            sm.sw[rank] = w[i];
+            nz++;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, d);
+    const uint32_t R = nz;
+    const uint32_t Tn = R > 1 ? R - 1 : 0;                   // mc:1013-1019
+    const uint32_t mapB = (2 * Tn + 7) / 8;                  // mc:1024-1026
+    __syncwarp();
+
+    uint32_t maxlen = 0;
+    if (lane == 0 && R >= 2) {
+        // ---- two-queue merge (mc:575-607): on equal weight a leaf, then the older internal node, goes first
+        const uint32_t base = 512 - R;                       // mc:569
+        uint32_t qa = 0, qb = 0, made = 0;
+        while ((R - qa) + (made - qb) > 1) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                bool leaf;
+                if (qa >= R) leaf = false;
+                else if (qb >= made) leaf = true;
+                else leaf = sm.sw[qa] <= sm.iw[qb];
+                if (leaf) { sm.child[2 * made + side] = sm.ssym[qa]; sum += sm.sw[qa]; qa++; }
+                else { sm.child[2 * made + side] = (uint16_t)(base + qb); sum += sm.iw[qb]; qb++; }
+            }
+            sm.iw[made] = sum;
+            made++;
+        }
+        // ---- codes: bit k = k-th branch from the root, 0 = left (mc:869-917) ------------------
+        sm.icode[Tn - 1] = 0; sm.ilen[Tn - 1] = 0;
+        for (int j = (int)Tn - 1; j >= 0; j--) {
+            const uint32_t pc = sm.icode[j], pl = sm.ilen[j];
+#pragma unroll
+            for (uint32_t side = 0; side < 2; side++) {
+                const uint32_t ci = sm.child[2 * j + side];
+                const uint32_t cc = pl < 32 ? (pc | (side << pl)) : pc;
+                const uint32_t cl = pl + 1;
+                if (ci < 256) {
+                    sm.tab[ci] = cl <= 31 ? (cc | (1u << cl)) : 0u;
+                    if (cl > maxlen) maxlen = cl;
+                } else {
+                    sm.icode[ci - base] = cc; sm.ilen[ci - base] = (uint8_t)cl;
+                }
+            }
+        }
+    }
+    maxlen = __shfl_sync(0xFFFFFFFFu, maxlen, 0);
+    // ---- serialised header: Tn | child-is-internal bitmap | (left,right) byte pairs ------------
+    for (uint32_t i = lane; i < 1 + mapB; i += 32) sm.hdr[i] = (i == 0) ? (uint8_t)Tn : (uint8_t)0;
+    __syncwarp();
+    if (lane == 0)
+        for (uint32_t j = 0; j < 2 * Tn; j++)
+            if (sm.child[j] >= 256) sm.hdr[1 + (j >> 3)] |= (uint8_t)(1u << (j & 7));   // mc:1035-1050
+    for (uint32_t j = lane; j < 2 * Tn; j += 32) {
+        const uint32_t ci = sm.child[j];
+        sm.hdr[1 + mapB + j] = (uint8_t)(ci >= 256 ? ci - 256 : ci);
+    }
+    __syncwarp();
+    const uint32_t hdrBytes = 1 + mapB + 2 * Tn;
+    for (uint32_t i = lane; i < hdrBytes; i += 32) ws.segHdr[(size_t)s * kSegHdrStride + i] = sm.hdr[i];
+    // ---- table out + total bits -----------------------------------------------------------------
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int sym = lane + 32 * i;
+        const uint32_t e = sm.tab[sym];
+        ws.segTab[(size_t)s * 256 + sym] = e;
+        if (e) bits += (unsigned long long)w[i] * (uint32_t)(31 - __clz(e));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
+    if (lane == 0) {
+        si[SI_R] = R;
+        si[SI_HDR] = hdrBytes;
+        si[SI_W] = (uint32_t)((bits + 31) >> 5);             // mc:895-923: ceil(totalBits/32) words
+        si[SI_MAXLEN] = maxlen;
+        if (maxlen > 31) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_CODELEN);
+    }
+}
+
+// =========================================================================================
+// per-chunk bit length = dot(chunk histogram, code length)
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+k_chunk_bits(Ws ws)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t nChunks = ws.totals[TOT_CHUNKS];
+    const uint32_t warpsPerGrid = gridDim.x * 8;
+    for (uint32_t chunk = blockIdx.x * 8 + (threadIdx.x >> 5); chunk < nChunks; chunk += warpsPerGrid) {
+        const uint32_t s = ws.chunkSeg[chunk];
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int sym = lane + 32 * i;
+            const uint32_t e = ws.segTab[(size_t)s * 256 + sym];
+            const uint32_t cntv = ws.chunkHist[(size_t)chunk * 256 + sym];
+            if (e) bits += cntv * (uint32_t)(31 - __clz(e));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
+        if (lane == 0) ws.chunkBits[chunk] = bits;
+    }
+}
+
+// chunk bit offsets inside each stream (<= 128 chunks per stream: one thread per stream)
+__global__ void __launch_bounds__(256)
+k_seg_scan(Ws ws, uint32_t nSeg)
+{
+    const uint32_t s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= nSeg) return;
+    const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+    const uint32_t first = si[SI_FIRST_CHUNK], nch = si[SI_NCHUNKS];
+    uint32_t off = 0;
+    for (uint32_t c = 0; c < nch; c++) {
+        ws.chunkBitOff[first + c] = off;
+        off += ws.chunkBits[first + c];
+    }
+    if (nch && ((off + 31) >> 5) != si[SI_W]) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_INTERNAL);
+}
+
+// =========================================================================================
+// payload sizes -> record offsets -> absolute bit position of every stream's code words
+// =========================================================================================
+__device__ __forceinline__ uint32_t section_bytes(const uint32_t *si)
+{
+    const uint32_t S = si[SI_S];
+    if (S == 0) return 0;
+    if (si[SI_RAW]) return S;
+    return si[SI_HDR] + 4 + 4 * si[SI_W];
+}
+
+__global__ void __launch_bounds__(1024)
+k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
+{
+    __shared__ unsigned long long warpSum[32];
+    __shared__ unsigned long long running;
+    __shared__ unsigned long long accSin, accSout, accTok, accMat;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        running = ws.counters[C_CURSOR] + (withHeader ? 10ull : 0ull);
+        accSin = accSout = accTok = accMat = 0;
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < nBlocks; base += 1024) {
+        const uint32_t b = base + tid;
+        unsigned long long rec = 0;
+        uint32_t sec[4] = {0, 0, 0, 0};
+        if (b < nBlocks) {
+            unsigned long long sin = 0, sout = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t *si = ws.segInfo + ((size_t)b * 4 + k) * SI_WORDS;
+                sec[k] = section_bytes(si);
+                if (si[SI_W]) { sin += si[SI_S]; sout += 4ull * si[SI_W]; }
+            }
+            rec = 4ull + 4 + sec[0] + sec[1] + 4 + sec[2] + 4 + sec[3];   // u32 size | payload (mc:4111-4114)
+            atomicAdd(&accSin, sin); atomicAdd(&accSout, sout);
+            atomicAdd(&accTok, (unsigned long long)ws.meta[(size_t)b * M_WORDS + M_T]);
+            atomicAdd(&accMat, (unsigned long long)ws.meta[(size_t)b * M_WORDS + M_PC]);
+        }
+        unsigned long long inc = rec;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warpSum[warp] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0, total = 0;
+        for (int w = 0; w < 32; w++) { unsigned long long v = warpSum[w]; if (w < warp) wbase += v; total += v; }
+        const unsigned long long off = running + wbase + inc - rec;
+        if (b < nBlocks) {
+            ws.blkOff[b] = off;
+            // absolute bit position of word 0 of each stream's code words
+            unsigned long long p = off + 4 + 4;                                  // size, T
+            for (int k = 0; k < 4; k++) {
+                const uint32_t *si = ws.segInfo + ((size_t)b * 4 + k) * SI_WORDS;
+                if (k == 2 || k == 3) p += 4;                                    // Pc before p section, G before Golomb section
+                ws.segBitBase[(size_t)b * 4 + k] = 8ull * (p + si[SI_HDR] + 4);
+                p += sec[k];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ws.blkOff[nBlocks] = running;
+        ws.counters[C_LAST_BYTES] = running - ws.counters[C_CURSOR];
+        ws.counters[C_CURSOR] = running;
+        ws.counters[C_SIN] += accSin; ws.counters[C_SOUT] += accSout;
+        ws.counters[C_TOKENS] += accTok; ws.counters[C_MATCHES] += accMat;
+        ws.counters[C_BLOCKS] += nBlocks;
+        if (running > outCap) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_CAPACITY);
+    }
+}
+
+// =========================================================================================
+// encode: the HBM-bound kernel (algorithmic bytes = S_in + S_out)
+// =========================================================================================
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_RUN = kChunkSyms / ENC_THREADS;     // 32 symbols per thread
+static_assert(ENC_RUN == 32, "run length is baked into the carry logic (>= 32 bits per run)");
+
+struct EncSmem {
+    uint32_t tab[256 * 32];            // tab[sym*32 + lane]: bank == lane, conflict-free lookups
+    uint32_t stage[kChunkSyms + 8];    // worst case 32 bits per symbol
+    uint32_t warpBits[8];
+    uint32_t warpTail[8];
+};
+
+size_t encode_smem_bytes() { return sizeof(EncSmem); }
+
+__global__ void __launch_bounds__(ENC_THREADS)
+k_encode(Ws ws, uint32_t *__restrict__ out32)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (ws.totals[TOT_ERR]) return;                     // capacity / internal error: write nothing
+    const uint32_t nChunks = ws.totals[TOT_CHUNKS];
+    uint32_t curSeg = 0xFFFFFFFFu;
+    for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+        const uint32_t s = ws.chunkSeg[chunk];
+        const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+        if (si[SI_W] == 0) continue;                    // single-symbol stream: zero bits (mc:859)
+        if (s != curSeg) {
+            __syncthreads();
+            const uint32_t *t = ws.segTab + (size_t)s * 256;
+            for (int idx = tid; idx < 256 * 32; idx += ENC_THREADS) sm.tab[idx] = t[idx >> 5];
+            curSeg = s;
+            __syncthreads();
+        }
+        const uint32_t b = s >> 2, k = s & 3;
+        const uint32_t c = chunk - si[SI_FIRST_CHUNK];
+        const uint32_t S = si[SI_S];
+        const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
+        const uint32_t nRuns = cnt / ENC_RUN;
+        const uint8_t *src = ws.strm[k] + (size_t)b * ws.strmStride[k] + (size_t)c * kChunkSyms;
+        const unsigned long long gb0 = ws.segBitBase[s] + ws.chunkBitOff[chunk];
+        const uint32_t r0 = (uint32_t)(gb0 & 31);
+        const unsigned long long gw0 = gb0 >> 5;
+        const bool active = (uint32_t)tid < nRuns;
+
+        uint32_t sy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (active) {
+            const uint4 a = reinterpret_cast<const uint4 *>(src)[tid * 2];
+            const uint4 d = reinterpret_cast<const uint4 *>(src)[tid * 2 + 1];
+            sy[0] = a.x; sy[1] = a.y; sy[2] = a.z; sy[3] = a.w;
+            sy[4] = d.x; sy[5] = d.y; sy[6] = d.z; sy[7] = d.w;
+        }
+        // ---- pass 1: bits of this run ------------------------------------------------------
+        uint32_t myBits = 0;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t sym = (sy[j >> 2] >> ((j & 3) * 8)) & 0xFF;
+                myBits += (uint32_t)(31 - __clz(sm.tab[sym * 32 + lane]));
+            }
+        }
+        uint32_t inc = myBits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) sm.warpBits[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, fullBits = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { uint32_t v = sm.warpBits[w]; if (w < warp) wbase += v; fullBits += v; }
+        const uint32_t p0 = r0 + wbase + inc - myBits;   // staging bit position of this run
+
+        // ---- pass 2: pack.  acc holds bits not yet flushed; the first flushed word (head) may
+        // share its low bits with the previous run's tail, which arrives by shuffle afterwards.
+        uint32_t headWord = 0, headIdx = 0, tail = 0, tailIdx = 0;
+        if (active) {
+            unsigned long long acc = 0;
+            uint32_t accBits = p0 & 31, w = p0 >> 5;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t sym = (sy[j >> 2] >> ((j & 3) * 8)) & 0xFF;
+                const uint32_t e = sm.tab[sym * 32 + lane];
+                const uint32_t len = (uint32_t)(31 - __clz(e));
+                acc |= (unsigned long long)(e ^ (1u << len)) << accBits;
+                accBits += len;
+                if (accBits >= 32) {
+                    if (first) { headWord = (uint32_t)acc; headIdx = w; first = false; }
+                    else sm.stage[w] = (uint32_t)acc;
+                    w++; acc >>= 32; accBits -= 32;
+                }
+            }
+            tail = (uint32_t)acc; tailIdx = w;
+        }
+        // tail of lane l-1 lives in the low bits of lane l's head word
+        uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+        if (lane == 31) sm.warpTail[warp] = tail;
+        if (active) {
+            if (lane > 0) headWord |= prevTail;
+            sm.stage[headIdx] = headWord;
+            if ((uint32_t)tid == nRuns - 1) sm.stage[tailIdx] = tail;   // nobody follows: park the tail
+        }
+        __syncthreads();
+        if (active && lane == 0 && warp > 0) sm.stage[headIdx] |= sm.warpTail[warp - 1];
+        __syncthreads();
+
+        // ---- copy out: whole words by plain coalesced stores, shared edge words by atomicOr ----
+        const uint32_t stageBits = r0 + fullBits;
+        const uint32_t nFull = stageBits >> 5, rem = stageBits & 31;
+        for (uint32_t j = tid; j < nFull; j += ENC_THREADS) {
+            if (j == 0 && r0) atomicOr(&out32[gw0], sm.stage[0]);
+            else out32[gw0 + j] = sm.stage[j];
+        }
+        if (tid == 0 && rem && nRuns) atomicOr(&out32[gw0 + nFull], sm.stage[nFull]);
+        // ---- ragged end of the stream (< 32 symbols): serial append ---------------------------
+        if (tid == 0 && cnt > nRuns * ENC_RUN) {
+            unsigned long long bp = gb0 + fullBits;
+            for (uint32_t i = nRuns * ENC_RUN; i < cnt; i++) {
+                const uint32_t e = sm.tab[(uint32_t)src[i] * 32];
+                const uint32_t len = (uint32_t)(31 - __clz(e));
+                const unsigned long long v = (unsigned long long)(e ^ (1u << len)) << (bp & 31);
+                atomicOr(&out32[bp >> 5], (uint32_t)v);
+                if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
+                bp += len;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =========================================================================================
+// headers: file header, record sizes, counters, serialised trees, raw bitmap byte
+// =========================================================================================
+__global__ void __launch_bounds__(128)
+k_headers(Ws ws, uint8_t *__restrict__ out, uint32_t nBlocks, uint32_t withHeader,
+          uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor)
+{
+    if (ws.totals[TOT_ERR]) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nBlocks) return;
+    if (b == 0 && withHeader && lane == 0) {
+        uint8_t *h = out + batchStartCursor;              // mc:101-109 packed header, rewritten at mc:4128-4129
+        h[0] = 'F'; h[1] = 'C'; h[2] = 'X'; h[3] = '7';
+        st_u32_bytes(h + 4, hdrTotalBytes);               // uInt32 cmp_before_bytes (wraps)
+        h[8] = (uint8_t)hdrBlocks; h[9] = (uint8_t)(hdrBlocks >> 8);   // uInt16 block_num (wraps)
+    }
+    const unsigned long long off = ws.blkOff[b];
+    const uint32_t *m = ws.meta + (size_t)b * M_WORDS;
+    uint8_t *q = out + off;
+    // payload size: next record offset is not known per block without a second array; recompute
+    uint32_t sec[4];
+    for (int k = 0; k < 4; k++) sec[k] = section_bytes(ws.segInfo + ((size_t)b * 4 + k) * SI_WORDS);
+    const uint32_t payload = 4 + sec[0] + sec[1] + 4 + sec[2] + 4 + sec[3];
+    if (lane == 0) { st_u32_bytes(q, payload); st_u32_bytes(q + 4, m[M_T]); }       // mc:4111, mc:2137-2139
+    q += 8;
+    for (int k = 0; k < 4; k++) {
+        const uint32_t s = b * 4 + k;
+        const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+        if (k == 2) { if (lane == 0) st_u32_bytes(q, m[M_PC]); q += 4; }             // mc:2186-2188
+        if (k == 3) { if (lane == 0) st_u32_bytes(q, m[M_G]); q += 4; }              // mc:2225-2227
+        const uint32_t S = si[SI_S];
+        if (S == 0) continue;
+        if (si[SI_RAW]) {                                                            // mc:2104-2107
+            const uint8_t *src = ws.strm[k] + (size_t)b * ws.strmStride[k];
+            for (uint32_t i = lane; i < S; i += 32) q[i] = src[i];
+        } else {
+            const uint32_t hb = si[SI_HDR];
+            const uint8_t *h = ws.segHdr + (size_t)s * kSegHdrStride;
+            for (uint32_t i = lane; i < hb; i += 32) q[i] = h[i];
+            if (lane == 0) st_u32_bytes(q + hb, si[SI_W]);                           // mc:1081
+        }
+        q += sec[k];
+    }
+}
+
+// =========================================================================================
+// launches
+// =========================================================================================
+void huff_init()
+{
+    cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+}
+
+int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
+                      uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
+                      cudaStream_t st, void (*mark)(void *, int), void *markArg)
+{
+    const uint32_t nSeg = nBlocks * 4;
+    int launches = 0;
+    cudaMemsetAsync(ws.segHist, 0, (size_t)nSeg * 256 * sizeof(uint32_t), st);
+    k_plan<<<1, 1024, 0, st>>>(ws, nBlocks); launches++;
+    k_fill_chunks<<<(nSeg * 32 + 255) / 256, 256, 0, st>>>(ws, nSeg); launches++;
+    if (mark) mark(markArg, 2);
+    k_hist<<<numSM * 8, 256, 0, st>>>(ws); launches++;
+    if (mark) mark(markArg, 3);
+    k_tree<<<(nSeg + TREE_WARPS - 1) / TREE_WARPS, TREE_WARPS * 32, 0, st>>>(ws, nSeg); launches++;
+    if (mark) mark(markArg, 4);
+    k_chunk_bits<<<numSM * 4, 256, 0, st>>>(ws); launches++;
+    k_seg_scan<<<(nSeg + 255) / 256, 256, 0, st>>>(ws, nSeg); launches++;
+    k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, withHeader, outCap); launches++;
+    if (mark) mark(markArg, 5);
+    k_encode<<<numSM * 3, ENC_THREADS, sizeof(EncSmem), st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
+    if (mark) mark(markArg, 6);
+    k_headers<<<(nBlocks + 3) / 4, 128, 0, st>>>(ws, out, nBlocks, withHeader, hdrTotalBytes, hdrBlocks, batchStartCursor);
+    launches++;
+    if (mark) mark(markArg, 7);
+    return launches;
+}
+
+} // namespace fcx

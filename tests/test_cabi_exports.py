@@ -1,0 +1,77 @@
+"""CPU-side checks of the boundary: libfcx.so loads, exports everything include/fcx.h declares,
+and refuses to compute without a CUDA device (there is no CPU fallback to fall into)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from my_compress_b200 import api, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    build.build()
+    return api.lib()
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "fcx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fcx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(L):
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "libfcx.so does not export %s" % n
+    assert sorted(api.EXPORTS) == names
+
+
+def test_compress_bound_covers_reference_worst_case(L):
+    # worst observed payload: random data ~1.0163 n; hard bound 9/8 n + trees + counters
+    for n in (0, 1, 1 << 20, (1 << 20) + 1, 64 << 20):
+        nb = (n + (1 << 20) - 1) >> 20
+        assert api.compress_bound(n) >= 10 + nb * (4 + 12 + 4 * 579) + n + n // 8
+
+
+def test_argument_errors(L):
+    out = np.zeros(64, np.uint8)
+    n = C.c_uint64(0)
+    assert L.fcx_compress_lz77(None, 5, out.ctypes.data, 64, C.byref(n), 1) == -1      # FCX_ERR_ARG (mc:2122 returns 0)
+    assert b"null" in L.fcx_last_error()
+    n32 = C.c_uint32(0)
+    assert L.fcx_compress_block_lz77(out.ctypes.data, 0, out.ctypes.data, 64, C.byref(n32)) == -1
+    assert L.fcx_compress_block_lz77(out.ctypes.data, (1 << 20) + 1, out.ctypes.data, 64, C.byref(n32)) == -1
+    bad = np.frombuffer(b"NOPE000000000000", np.uint8)
+    assert L.fcx_decompress_lz77(bad.ctypes.data, len(bad), out.ctypes.data, 64, C.byref(n), 1) == -5   # mc:4146-4152
+    fcx8 = np.frombuffer(b"FCX8" + bytes(12), np.uint8)
+    assert L.fcx_decompress_lz77(fcx8.ctypes.data, len(fcx8), out.ctypes.data, 64, C.byref(n), 1) == -6
+
+
+def test_no_cpu_fallback_without_device(L):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    assert L.fcx_device_count() == 0
+    x = np.arange(100, dtype=np.uint8)
+    out = np.zeros(4096, np.uint8)
+    n = C.c_uint64(0)
+    assert L.fcx_compress_lz77(x.ctypes.data, 100, out.ctypes.data, 4096, C.byref(n), 1) == -2          # FCX_ERR_NO_DEVICE
+    ctx = C.c_void_p(None)
+    assert L.fcx_ctx_create(C.byref(ctx), 0, 4) == -2
+    with pytest.raises(api.FcxError):
+        api.compress(b"hello world")
+
+
+def test_randm_generator_is_a_flat_permutation(L):
+    # 随机数的生成.cpp:26-42: a permutation of [0,m); low bytes are exactly flat when 256 | m
+    b = api.datagen_randm(1 << 16, 20261018)
+    assert np.array_equal(np.bincount(b, minlength=256), np.full(256, 256))
+    assert np.array_equal(b, api.datagen_randm(1 << 16, 20261018))
+    assert not np.array_equal(b, api.datagen_randm(1 << 16, 7))

@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA path (through the C ABI in libfcx.so) against the oracle port,
+stage by stage and end to end.  Integer/byte work: bit-exact, no tolerance."""
+import hashlib
+import json
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from _cases import small_buffers, stream_buffers
+from _libs import oracle
+from my_compress_b200 import api, datagen
+
+pytestmark = pytest.mark.gpu
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+@pytest.fixture(scope="module")
+def dc():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    d = api.DeviceCompressor(0, max_batch_blocks=8)
+    yield d
+    d.close()
+
+
+def _dev(buf):
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(buf, dtype=np.uint8)).cuda()
+    pad = torch.zeros(((t.numel() + 15) // 16) * 16 + 16, dtype=torch.uint8, device="cuda")
+    pad[: t.numel()] = t
+    return pad[: t.numel()]
+
+
+def _first_diff(a, b):
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            return i
+    return n
+
+
+def test_match_every_position(dc):
+    o = oracle()
+    bufs = [(n, b) for n, b in small_buffers() if len(b) > 0]
+    bufs.append(("zipf64k", datagen.zipf_block(65536, 1, 0)))
+    bufs.append(("phrases100k", datagen.phrases_block(100000, 1, 0)))
+    bufs.append(("zeros20k", np.zeros(20000, np.uint8)))
+    bufs.append(("uniform30k", datagen.uniform_block(30000, 1, 0)))
+    for name, buf in bufs:
+        po, lo = o.match_all(buf)
+        lg, pg = dc.probe_match(_dev(buf))
+        bad = np.nonzero((lg != lo) | (pg != po))[0]
+        assert len(bad) == 0, "%s: first mismatch at %d: gpu (p=%d,l=%d) oracle (p=%d,l=%d)" % (
+            name, bad[0], pg[bad[0]], lg[bad[0]], po[bad[0]], lo[bad[0]])
+
+
+def _oracle_streams(buf):
+    o = oracle()
+    p, l, c = o.lz77_parse(buf)
+    T = len(c)
+    bm = np.zeros((T + 7) // 8, np.uint8)
+    lit = np.nonzero(l == 0)[0]
+    np.bitwise_or.at(bm, lit >> 3, (1 << (lit & 7)).astype(np.uint8))
+    m = l != 0
+    gw = o.golomb_encode(l[m])
+    return {"T": T, "Pc": int(m.sum()), "G": len(gw), "bitmap": bm.tobytes(), "c": c.tobytes(),
+            "p": o.combine_bits(p[m]), "golomb": gw.tobytes()}
+
+
+def test_parse_and_stream_split(dc):
+    bufs = [(n, b) for n, b in small_buffers(seed=4321) if len(b) > 0]
+    bufs.append(("zipf300k", datagen.zipf_block(300000, 2, 0)))
+    bufs.append(("phrases1M", datagen.phrases_block(1 << 20, 2, 0)))
+    bufs.append(("uniform70k", datagen.uniform_block(70000, 2, 0)))
+    bufs.append(("byterun9000", datagen.byte_run_block(9000, 6, 0)))
+    for name, buf in bufs:
+        want = _oracle_streams(buf)
+        got = dc.probe_streams(_dev(buf))
+        for k in ("T", "Pc", "G"):
+            assert got[k] == want[k], (name, k, got[k], want[k])
+        for k in ("bitmap", "c", "p", "golomb"):
+            assert got[k] == want[k], "%s: stream %s differs at byte %d" % (name, k, _first_diff(got[k], want[k]))
+
+
+def test_huffman_section_bytes(dc):
+    o = oracle()
+    bufs = list(stream_buffers())
+    bufs.append(("uniform1M", datagen.uniform_block(1 << 20, 7, 0)))
+    bufs.append(("zipf500001", datagen.zipf_block(500001, 7, 0)))
+    bufs.append(("bits8192", np.random.default_rng(5).integers(0, 2, size=8192, dtype=np.uint8)))
+    bufs.append(("bits8193", np.random.default_rng(5).integers(0, 2, size=8193, dtype=np.uint8)))
+    bufs.append(("skew24577", np.minimum(np.random.default_rng(6).geometric(0.5, size=24577) - 1, 255).astype(np.uint8)))
+    for name, s in bufs:
+        want = o.huffman_section(s)
+        got = dc.probe_huffman_section(_dev(s))
+        assert got == want, "%s: section differs at byte %d of %d/%d" % (name, _first_diff(got, want), len(got), len(want))
+
+
+def test_block_payloads_vs_oracle_and_golden():
+    o = oracle()
+    for name, buf in small_buffers(seed=2024):
+        if len(buf) == 0:
+            continue
+        want = o.compress_block(buf)
+        got = api.my_compress_file_lz77(buf)
+        assert got == want, "%s: payload differs at byte %d" % (name, _first_diff(got, want))
+    for b in G["blocks"]:
+        x = datagen.gen_block(b["family"], b["n"], b["seed"], 0)
+        got = api.my_compress_file_lz77(x)
+        assert len(got) == b["payload_bytes"] and hashlib.sha256(got).hexdigest() == b["payload_sha256"], b
+
+
+def test_golden_files():
+    f = G["file_small"]
+    assert api.compress(f["in"].encode()).hex() == f["fcx7_hex"]
+    assert api.compress(np.full(5000, 65, np.uint8)).hex() == G["file_A5000"]["fcx7_hex"]
+    assert api.compress(b"").hex() == G["file_empty"]["fcx7_hex"]
+    t = G["file_two_blocks"]
+    data = np.concatenate([datagen.phrases_block(1 << 20, 3, 0), datagen.zipf_block(70000, 3, 1)])
+    blob = api.compress(data)
+    assert len(blob) == t["bytes"] and hashlib.sha256(blob).hexdigest() == t["sha256"]
+
+
+def _oracle_container(data):
+    """Oracle container with the per-block work fanned out over host threads (ctypes drops the GIL)."""
+    o = oracle()
+    n = len(data)
+    nb = (n + (1 << 20) - 1) >> 20
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
+        payloads = list(ex.map(lambda b: o.compress_block(data[b << 20 : min(n, (b + 1) << 20)]), range(nb)))
+    head = b"FCX7" + (n & 0xFFFFFFFF).to_bytes(4, "little") + (nb & 0xFFFF).to_bytes(2, "little")
+    return head + b"".join(len(p).to_bytes(4, "little") + p for p in payloads)
+
+
+@pytest.mark.parametrize("family,nbytes", [
+    ("randm", 1 << 20),                  # config 1
+    ("zipf", (8 << 20) + 12345),         # config 2 family, ragged tail
+    ("phrases", 16 << 20),               # config 3 family
+    ("mixed", 12 << 20),                 # config 4 family
+    ("uniform", (4 << 20) + 1),          # config 5 family, 1-byte last block
+    ("byterun", (1 << 20) + 5000),       # worst case for the match finder
+    ("periodic", 3 << 20),
+])
+def test_container_vs_oracle(family, nbytes):
+    data = datagen.gen(family, nbytes, seed=11)
+    want = _oracle_container(data)
+    got = api.compress(data)
+    assert len(got) == len(want), (len(got), len(want))
+    assert got == want, "container differs at byte %d" % _first_diff(got, want)
+
+
+def test_decompress_matches_reference_behaviour():
+    o = oracle()
+    cases = [b"A" * 5000, b"\0" * 4000, b"x", bytes(range(64)), b"aacaacabcabaaacbaaacccaacabcad"]
+    for name, buf in small_buffers(seed=31, count=24, max_len=4000):
+        if len(buf):
+            cases.append(buf.tobytes())
+    for data in cases:
+        payload = o.compress_block(np.frombuffer(data, np.uint8))
+        want = o.decompress_block(payload)
+        got = api.my_decompress_file_lz77(payload)
+        assert got == want, data[:16]
+
+
+def test_round_trip_container():
+    for family, nbytes in (("zipf", (2 << 20) + 77), ("phrases", 3 << 20), ("uniform", 1 << 20)):
+        data = datagen.gen(family, nbytes, seed=5)
+        blob = api.compress(data)
+        assert api.decompress(blob) == data.tobytes()
