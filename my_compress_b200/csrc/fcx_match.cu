@@ -6,46 +6,85 @@
 //   among s in [max(0,i-2047), i-1]: maximise min(cap, LCP(x[s..], x[i..])) (overlap allowed),
 //   ties -> smallest s (farthest);  result kept only when >= 3.
 //
-// One CTA owns a tile of 6144 positions and stages tile + 2048 bytes of history + 272 bytes
-// of look-ahead in shared memory.  The 8192-slot region is cut into eight 1024-slot
+// One CTA owns a tile of 4096 positions and stages tile + 2048 bytes of history + 272 bytes
+// of look-ahead in shared memory.  The 6144-slot region is cut into six 1024-slot
 // sub-regions; warp w threads the positions of sub-region w into ASCENDING per-hash chains
 // (hash of the 3-byte gram) with __match_any_sync, walking its chunks from the top so that
-// head[] ends up holding the lowest slot and up[] the next higher slot of the same hash.
+// head[] ends up holding the lowest slot and up[] the next higher slot of the same hash;
+// head[] also carries the bucket population.
 // A position then walks the chains of the (at most three) sub-regions overlapping its
 // window from the far end towards itself: strict '>' on the length gives the reference's
 // farthest-wins tie rule, a candidate is only extended when the byte at the current best
 // length matches, and a hit of the cap ends the walk (nothing nearer can beat it).
+//
+// Chain lengths differ wildly between neighbouring positions (a hot Zipf gram has hundreds
+// of candidates, its neighbour none); with one position per lane that left ~5 of 32 lanes
+// busy.  So when a tile has long chains its positions are first counting-sorted by estimated
+// chain length (bucket populations, half-octave bins, heaviest first) and lanes take
+// consecutive entries of that order: neighbouring lanes then walk chains of similar length.
 #include "fcx_dev.cuh"
 
 namespace fcx {
 
-constexpr int MT_TILE = 6144;
+constexpr int MT_TILE = 4096;
 constexpr int MT_SUB = 1024;
 constexpr int MT_HALO = 2048;
-constexpr int MT_REGION = MT_TILE + MT_HALO;     // 8192 slots
-constexpr int MT_NSUB = MT_REGION / MT_SUB;      // 8
-constexpr int MT_HBITS = 11;
+constexpr int MT_REGION = MT_TILE + MT_HALO;     // 6144 slots
+constexpr int MT_NSUB = MT_REGION / MT_SUB;      // 6
+constexpr int MT_HBITS = 10;
 constexpr int MT_HB = 1 << MT_HBITS;             // buckets per sub-region
 constexpr int MT_LOOK = 272;                     // >= 257 + 8
 constexpr int MT_THREADS = 256;
-constexpr uint16_t MT_NONE = 0xFFFF;
+constexpr int MT_PER_THREAD = MT_TILE / MT_THREADS;   // 16
+constexpr uint32_t MT_NONE = 0xFFFF;
+constexpr int MT_BINS = 32;
+constexpr uint32_t MT_SORT_THRESHOLD = 6;        // sort only when some bucket holds more than this
 
 struct MatchSmem {
     uint32_t xs[(MT_REGION + MT_LOOK) / 4];
-    uint16_t head[MT_NSUB * MT_HB];
+    uint32_t head[MT_NSUB * MT_HB];              // low 16: lowest slot (0xFFFF none), high 16: population
     uint16_t up[MT_REGION];
+    uint16_t order[MT_TILE];
+    uint8_t bin[MT_TILE];
+    uint32_t binCount[MT_BINS];
+    uint32_t binStart[MT_BINS];
+    uint32_t maxPop;
 };
 
-int match_tiles_per_block() { return (kBlockBytes + MT_TILE - 1) / MT_TILE; }
-size_t match_smem_bytes() { return sizeof(MatchSmem); }
+// ---- explicit shared-memory loads (32-bit shared addresses held in registers) -------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// unaligned little-endian 32-bit read at shared byte address a
+__device__ __forceinline__ uint32_t lds_u32_unaligned(uint32_t a)
+{
+    const uint32_t al = a & ~3u;
+    return __funnelshift_r(lds_u32(al), lds_u32(al + 4), (a & 3u) * 8);
+}
 
-__device__ __forceinline__ int lcp_capped(const uint32_t *xs, int a, int b, int cap)
+__device__ __forceinline__ int lcp_capped(uint32_t xsA, int a, int b, int cap)
 {
     int k = 0;
     while (k < cap) {
-        uint32_t d = ld32u(xs, a + k) ^ ld32u(xs, b + k);
+        const uint32_t d = lds_u32_unaligned(xsA + a + k) ^ lds_u32_unaligned(xsA + b + k);
         if (d) {
-            int m = k + ((__ffs(d) - 1) >> 3);
+            const int m = k + ((__ffs(d) - 1) >> 3);
             return m < cap ? m : cap;
         }
         k += 4;
@@ -85,14 +124,16 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         }
         reinterpret_cast<uint4 *>(sm.xs)[v] = q;
     }
-    for (int k = tid; k < MT_NSUB * MT_HB / 2; k += MT_THREADS)
-        reinterpret_cast<uint32_t *>(sm.head)[k] = 0xFFFFFFFFu;
+    for (int k = tid; k < MT_NSUB * MT_HB; k += MT_THREADS) sm.head[k] = MT_NONE;
+    if (tid < MT_BINS) sm.binCount[tid] = 0;
+    if (tid == 0) sm.maxPop = 0;
     __syncthreads();
 
     // ---- ascending hash chains, one warp per sub-region ---------------------------------
-    {
+    if (warp < MT_NSUB) {
         const int sr = warp;
-        uint16_t *head = sm.head + sr * MT_HB;
+        uint32_t *head = sm.head + sr * MT_HB;
+        uint32_t myMax = 0;
         for (int ch = MT_SUB / 32 - 1; ch >= 0; ch--) {
             const int slot = sr * MT_SUB + ch * 32 + lane;
             const int pos = regionBase + slot;
@@ -101,44 +142,99 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const uint32_t key = valid ? h : (0x80000000u | lane);
             const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
             const uint32_t higher = (lane == 31) ? 0u : (grp & ~((2u << lane) - 1u));
-            uint16_t old = MT_NONE;
+            uint32_t old = MT_NONE;
             if (valid) old = head[h];
             __syncwarp();
             if (valid) {
-                sm.up[slot] = higher ? (uint16_t)(sr * MT_SUB + ch * 32 + (__ffs(higher) - 1)) : old;
-                if ((grp & ((1u << lane) - 1u)) == 0) head[h] = (uint16_t)slot;
+                sm.up[slot] = higher ? (uint16_t)(sr * MT_SUB + ch * 32 + (__ffs(higher) - 1)) : (uint16_t)(old & 0xFFFF);
+                if ((grp & ((1u << lane) - 1u)) == 0) {
+                    const uint32_t pop = (old >> 16) + __popc(grp);
+                    head[h] = (uint32_t)slot | (pop << 16);
+                    myMax = max(myMax, pop);
+                }
             }
             __syncwarp();
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) myMax = max(myMax, __shfl_xor_sync(0xFFFFFFFFu, myMax, d));
+        if (lane == 0) atomicMax(&sm.maxPop, myMax);
     }
     __syncthreads();
 
+    const uint32_t xsA = smem_addr(sm.xs), headA = smem_addr(sm.head), upA = smem_addr(sm.up);
+    const int minSlot = -regionBase;                       // slot of block position 0
+    const int slotEnd = n - regionBase;                    // slot of block position n
+    const int tileSlots = min(MT_TILE, slotEnd - MT_HALO); // positions of this tile that exist
+    const bool sorted = sm.maxPop > MT_SORT_THRESHOLD;
+
+    // ---- balance: counting sort of the tile's positions by estimated chain length --------------
+    if (sorted) {
+        for (int k = 0; k < MT_PER_THREAD; k++) {
+            const int idx = k * MT_THREADS + tid;
+            const int si = MT_HALO + idx;
+            uint32_t bn = 0xFF;
+            if (idx < tileSlots) {
+                const uint32_t h = hash24(lds_u32_unaligned(xsA + si), MT_HBITS);
+                const int lo = max(si - kWindow, minSlot);
+                uint32_t est = 0;
+                for (int sr = lo >> 10; sr <= (si >> 10); sr++) est += lds_u32(headA + 4 * (sr * MT_HB + h)) >> 16;
+                bn = 0;                                    // half-octave bins of the estimate
+                if (est) {
+                    const int msb = 31 - __clz(est);
+                    const int half = msb > 0 ? (int)((est >> (msb - 1)) & 1u) : 0;
+                    bn = (uint32_t)min(MT_BINS - 1, 1 + 2 * msb + half);
+                }
+                sm.bin[idx] = (uint8_t)bn;
+            }
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
+            if (bn != 0xFF && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&sm.binCount[bn], (uint32_t)__popc(grp));
+        }
+        __syncthreads();
+        if (tid == 0) {                                    // heaviest bin first
+            uint32_t acc = 0;
+            for (int bn = MT_BINS - 1; bn >= 0; bn--) { sm.binStart[bn] = acc; acc += sm.binCount[bn]; }
+        }
+        __syncthreads();
+        for (int k = 0; k < MT_PER_THREAD; k++) {
+            const int idx = k * MT_THREADS + tid;
+            const uint32_t bn = idx < tileSlots ? (uint32_t)sm.bin[idx] : 0xFFu;
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
+            const int leader = __ffs(grp) - 1;
+            uint32_t base = 0;
+            if (bn != 0xFF && lane == leader) base = atomicAdd(&sm.binStart[bn], (uint32_t)__popc(grp));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (bn != 0xFF) sm.order[base + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)(MT_HALO + idx);
+        }
+        __syncthreads();
+    }
+
     // ---- per-position walk ----------------------------------------------------------------
     const size_t outBase = (size_t)b * kBlockBytes;
-    for (int k = 0; k < MT_TILE / MT_THREADS; k++) {
-        const int si = MT_HALO + k * MT_THREADS + tid;
+    const uint32_t orderA = smem_addr(sm.order);
+    for (int k = 0; k < MT_PER_THREAD; k++) {
+        const int idx = k * MT_THREADS + tid;
+        if (idx >= tileSlots) break;
+        const int si = sorted ? (int)lds_u16(orderA + 2 * idx) : MT_HALO + idx;
         const int i = regionBase + si;
-        if (i >= n) break;
-        int cap = n - 1 - i;
-        if (cap > kMaxLen) cap = kMaxLen;
+        const int cap = min(kMaxLen, n - 1 - i);
         int bestL = kMinLen - 1, bestS = 0;
         if (i > 0 && cap >= kMinLen) {
-            const uint32_t h = hash24(ld32u(sm.xs, si), MT_HBITS);
-            int lo = si - kWindow;
-            if (lo < -regionBase) lo = -regionBase;     // block position 0
-            const uint8_t *xb = reinterpret_cast<const uint8_t *>(sm.xs);
+            const uint32_t h = hash24(lds_u32_unaligned(xsA + si), MT_HBITS);
+            const int lo = max(si - kWindow, minSlot);
+            const uint32_t xi = xsA + si;
             bool done = false;
             for (int sr = lo >> 10; sr <= (si >> 10) && !done; sr++) {
-                int s = sm.head[sr * MT_HB + h];
-                while (s != MT_NONE && s < si) {
-                    if (s >= lo && xb[s + bestL] == xb[si + bestL]) {
-                        int L = lcp_capped(sm.xs, s, si, cap);
+                int s = (int)(lds_u32(headA + 4 * (sr * MT_HB + h)) & 0xFFFF);
+                while (s != (int)MT_NONE && s < si) {
+                    const int cur = s;
+                    s = (int)lds_u16(upA + 2 * cur);
+                    if (cur >= lo && lds_u8(xsA + cur + bestL) == lds_u8(xi + bestL)) {
+                        const int L = lcp_capped(xsA, cur, si, cap);
                         if (L > bestL) {
-                            bestL = L; bestS = s;
-                            if (L == cap) { done = true; break; }
+                            bestL = L; bestS = cur;
+                            if (L == cap) { done = true; break; }   // nothing nearer can beat the cap
                         }
                     }
-                    s = sm.up[s];
                 }
             }
         }
@@ -147,6 +243,9 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         dist[outBase + i] = hit ? (uint16_t)(si - bestS) : (uint16_t)0;
     }
 }
+
+int match_tiles_per_block() { return (kBlockBytes + MT_TILE - 1) / MT_TILE; }
+size_t match_smem_bytes() { return sizeof(MatchSmem); }
 
 // per device: opt in to > 48 KB of dynamic shared memory
 void match_init()
