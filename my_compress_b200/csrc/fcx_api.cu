@@ -23,7 +23,7 @@ void launch_match(const uint8_t *in, const uint32_t *blkLen, uint8_t *lenCode, u
                   uint32_t maxLen, cudaStream_t st);
 void match_init();
 // fcx_parse.cu
-void launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32_t nBlocks, cudaStream_t st);
+int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32_t nBlocks, uint32_t maxLen, cudaStream_t st);
 // fcx_huff.cu
 void huff_init();
 int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
@@ -135,6 +135,9 @@ extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks
     A(dalloc(c, &w.lenCode, B * kBlockBytes));
     A(dalloc(c, &w.dist, B * kBlockBytes));
     for (int k = 0; k < 4; k++) { w.strmStride[k] = seg_stride(k); A(dalloc(c, &w.strm[k], B * seg_stride(k))); }
+    A(dalloc(c, &w.parseExit, B * kParseTilesPerBlock * kParseEntries));
+    A(dalloc(c, &w.tileEntry, B * kParseTilesPerBlock));
+    A(dalloc(c, &w.tileCnt, B * kParseTilesPerBlock));
     A(dalloc(c, &w.blkLen, B));
     A(dalloc(c, &w.meta, B * M_WORDS));
     A(dalloc(c, &w.segHist, B * 4 * 256));
@@ -264,9 +267,8 @@ static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_o
         k_set_blklen<<<(nb + 255) / 256, 256, 0, st>>>(w.blkLen, n, (uint32_t)first, nb);
         launch_match(bin, w.blkLen, w.lenCode, w.dist, nb, maxLen, st);
         mark_stage(c, ST_MATCH);
-        launch_parse(bin, w.blkLen, w, nb, st);
+        c->launches += 2 + launch_parse(bin, w.blkLen, w, nb, maxLen, st);
         mark_stage(c, ST_PARSE);
-        c->launches += 3;
         c->launches += launch_huff_stage(w, nb, d_out, outCap, withHeader, (uint32_t)hdrBytes, hdrBlocks, 0, c->numSM, st,
                                          mark_stage, c);
         CK(cudaGetLastError());
@@ -554,8 +556,7 @@ extern "C" int fcx_probe_streams(fcx_ctx *c, const uint8_t *d_in, uint32_t n, ui
     cudaStream_t st = c->stream;
     k_set_blklen<<<1, 256, 0, st>>>(c->ws.blkLen, n, 0, 1);
     launch_match(d_in, c->ws.blkLen, c->ws.lenCode, c->ws.dist, 1, n, st);
-    launch_parse(d_in, c->ws.blkLen, c->ws, 1, st);
-    c->launches += 3;
+    c->launches += 2 + launch_parse(d_in, c->ws.blkLen, c->ws, 1, n, st);
     uint32_t m[M_WORDS];
     CK(cudaMemcpyAsync(m, c->ws.meta, sizeof(m), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -26,6 +26,11 @@ constexpr uint32_t kSegStride1 = 1048576 + 256;
 constexpr uint32_t kSegStride2 = 360704 + 256;
 constexpr uint32_t kSegStride3 = 105216 + 256;
 
+// ---- parse tiling -----------------------------------------------------------------------
+constexpr int kParseTile = 4096;                                  // positions per parse tile
+constexpr int kParseTilesPerBlock = kBlockBytes / kParseTile;     // 256
+constexpr int kParseEntries = 258;                                // a chain enters a tile at offset 0..257
+
 // ---- Huffman chunking ------------------------------------------------------------------
 constexpr int kChunkSyms = 8192;                  // symbols per encode/histogram chunk
 constexpr int kMaxChunksPerBlock = 128 + 17 + 45 + 14;   // c, bitmap, p, golomb (ceil + 1)
@@ -50,6 +55,9 @@ struct Ws {
     uint16_t *dist;       // [maxBlocks][1 MiB]
     uint8_t *strm[4];     // [maxBlocks][stride]
     uint32_t strmStride[4];
+    uint16_t *parseExit;  // [maxBlocks][256 tiles][258] exit offset (0..257) of a tile per entry offset
+    uint16_t *tileEntry;  // [maxBlocks][256] offset at which the chain enters each tile
+    uint4 *tileCnt;       // [maxBlocks][256] tokens, matches, Golomb bits (exclusive ranks after the scan)
     uint32_t *blkLen;     // [maxBlocks]
     uint32_t *meta;       // [maxBlocks][M_WORDS]
     uint32_t *segHist;    // [4*maxBlocks][256]

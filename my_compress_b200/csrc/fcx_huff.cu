@@ -371,36 +371,108 @@ k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
 // =========================================================================================
 // encode: the HBM-bound kernel (algorithmic bytes = S_in + S_out)
 // =========================================================================================
+// One CTA encodes a contiguous range of 8192-symbol chunks.  Each thread owns a run of 32
+// consecutive symbols (two 16-byte loads).  Pass 1 looks every symbol up once in a table that
+// is replicated 32x in shared memory (tab[sym*32 + lane]: bank == lane, conflict-free) and
+// keeps the 32 entries in registers; a CTA scan of the run lengths gives every run its bit
+// position.  Pass 2 packs from registers: codes are first merged GROUP at a time in a 32-bit
+// word (4 symbols when no code is longer than 8 bits, 2 up to 16, 1 up to 24), then inserted
+// into a 64-bit accumulator whose low word is flushed to a shared staging buffer.  A run is
+// >= 32 bits, so a staging word has at most two writers: the tail of run t travels by shuffle
+// into the first word of run t+1 -- no atomics inside the CTA.  The staged words go out as
+// coalesced 4-byte stores; only the first/last word of a chunk (shared with the neighbouring
+// chunk or with header bytes) is merged with atomicOr on the pre-zeroed container.
 constexpr int ENC_THREADS = 256;
 constexpr int ENC_RUN = kChunkSyms / ENC_THREADS;     // 32 symbols per thread
 static_assert(ENC_RUN == 32, "run length is baked into the carry logic (>= 32 bits per run)");
+constexpr int ENC_STAGE_WORDS = 4064;                 // 16 bits per symbol on average; denser chunks take the slow path
 
 struct EncSmem {
-    uint32_t tab[256 * 32];            // tab[sym*32 + lane]: bank == lane, conflict-free lookups
-    uint32_t stage[kChunkSyms + 8];    // worst case 32 bits per symbol
+    uint32_t tab[256 * 32];            // fast path: code | len<<24; generic path: code | 1<<len
+    uint32_t stage[ENC_STAGE_WORDS + 8];
     uint32_t warpBits[8];
     uint32_t warpTail[8];
 };
 
 size_t encode_smem_bytes() { return sizeof(EncSmem); }
 
+__device__ __forceinline__ uint32_t enc_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t enc_lds(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void enc_sts(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+// pack 32 table entries (code | len<<24) starting at staging bit p0; returns tail bits / word index
+template <int GROUP>
+__device__ __forceinline__ void enc_pack_fast(const uint32_t (&ent)[32], uint32_t p0, uint32_t stageA,
+                                              uint32_t &tail, uint32_t &tailIdx)
+{
+    uint32_t lo = 0, hi = 0, accBits = p0 & 31, w = stageA + 4 * (p0 >> 5);
+#pragma unroll
+    for (int j = 0; j < 32; j += GROUP) {
+        uint32_t g = 0, gl = 0;
+#pragma unroll
+        for (int k = 0; k < GROUP; k++) {
+            const uint32_t e = ent[j + k];
+            g |= (e & 0xFFFFFFu) << gl;
+            gl += e >> 24;
+        }
+        lo |= g << accBits;
+        hi |= __funnelshift_l(g, 0u, accBits);     // bits of g that spill past bit 31 (0 when accBits == 0)
+        accBits += gl;
+        if (accBits >= 32) { enc_sts(w, lo); w += 4; lo = hi; hi = 0; accBits -= 32; }
+    }
+    tail = lo; tailIdx = (w - stageA) >> 2;
+}
+
+// generic path, sentinel entries (code | 1<<len, len <= 31): one 64-bit insert per symbol
+__device__ __forceinline__ void enc_pack_generic(const uint32_t (&ent)[32], uint32_t p0, uint32_t stageA,
+                                                 uint32_t &tail, uint32_t &tailIdx)
+{
+    unsigned long long acc = 0;
+    uint32_t accBits = p0 & 31, w = stageA + 4 * (p0 >> 5);
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint32_t e = ent[j];
+        const uint32_t len = (uint32_t)(31 - __clz(e));
+        acc |= (unsigned long long)(e ^ (1u << len)) << accBits;
+        accBits += len;
+        if (accBits >= 32) { enc_sts(w, (uint32_t)acc); w += 4; acc >>= 32; accBits -= 32; }
+    }
+    tail = (uint32_t)acc; tailIdx = (w - stageA) >> 2;
+}
+
 __global__ void __launch_bounds__(ENC_THREADS)
 k_encode(Ws ws, uint32_t *__restrict__ out32)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
+    __shared__ EncSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (ws.totals[TOT_ERR]) return;                     // capacity / internal error: write nothing
     const uint32_t nChunks = ws.totals[TOT_CHUNKS];
+    const uint32_t per = (nChunks + gridDim.x - 1) / gridDim.x;
+    const uint32_t cBeg = blockIdx.x * per, cEnd = min(nChunks, cBeg + per);
+    const uint32_t tabLane = enc_smem_addr(sm.tab) + 4 * lane, stageA = enc_smem_addr(sm.stage);
     uint32_t curSeg = 0xFFFFFFFFu;
-    for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+    uint32_t mode = 0;                                  // 4/2/1: fast path group size, 0: generic
+    for (uint32_t chunk = cBeg; chunk < cEnd; chunk++) {
         const uint32_t s = ws.chunkSeg[chunk];
         const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
         if (si[SI_W] == 0) continue;                    // single-symbol stream: zero bits (mc:859)
         if (s != curSeg) {
+            const uint32_t maxlen = si[SI_MAXLEN];
+            mode = maxlen <= 8 ? 4u : maxlen <= 16 ? 2u : maxlen <= 24 ? 1u : 0u;
             __syncthreads();
-            const uint32_t *t = ws.segTab + (size_t)s * 256;
-            for (int idx = tid; idx < 256 * 32; idx += ENC_THREADS) sm.tab[idx] = t[idx >> 5];
+            uint32_t e = ws.segTab[(size_t)s * 256 + tid];      // ENC_THREADS == 256 symbols
+            if (mode && e) { const uint32_t len = (uint32_t)(31 - __clz(e)); e = (e ^ (1u << len)) | (len << 24); }
+            if (!mode && !e) e = 1;                              // absent symbol: zero-length sentinel (never looked up)
+#pragma unroll 8
+            for (int c = 0; c < 32; c++) sm.tab[tid * 32 + ((c + lane) & 31)] = e;
             curSeg = s;
             __syncthreads();
         }
@@ -414,22 +486,30 @@ k_encode(Ws ws, uint32_t *__restrict__ out32)
         const uint32_t r0 = (uint32_t)(gb0 & 31);
         const unsigned long long gw0 = gb0 >> 5;
         const bool active = (uint32_t)tid < nRuns;
+        const bool dense = r0 + ws.chunkBits[chunk] > (uint32_t)ENC_STAGE_WORDS * 32;   // does not fit the stage
 
-        uint32_t sy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // ---- pass 1: one lookup per symbol, entries stay in registers ------------------------
+        uint32_t ent[32];
+        uint32_t myBits = 0;
         if (active) {
             const uint4 a = reinterpret_cast<const uint4 *>(src)[tid * 2];
             const uint4 d = reinterpret_cast<const uint4 *>(src)[tid * 2 + 1];
-            sy[0] = a.x; sy[1] = a.y; sy[2] = a.z; sy[3] = a.w;
-            sy[4] = d.x; sy[5] = d.y; sy[6] = d.z; sy[7] = d.w;
-        }
-        // ---- pass 1: bits of this run ------------------------------------------------------
-        uint32_t myBits = 0;
-        if (active) {
+            const uint32_t sy[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const uint32_t sym = (sy[j >> 2] >> ((j & 3) * 8)) & 0xFF;
-                myBits += (uint32_t)(31 - __clz(sm.tab[sym * 32 + lane]));
+                ent[j] = enc_lds(tabLane + sym * 128);
             }
+            if (mode) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) myBits += ent[j] >> 24;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) myBits += (uint32_t)(31 - __clz(ent[j]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) ent[j] = mode ? 0u : 1u;
         }
         uint32_t inc = myBits;
 #pragma unroll
@@ -444,56 +524,58 @@ k_encode(Ws ws, uint32_t *__restrict__ out32)
         for (int w = 0; w < 8; w++) { uint32_t v = sm.warpBits[w]; if (w < warp) wbase += v; fullBits += v; }
         const uint32_t p0 = r0 + wbase + inc - myBits;   // staging bit position of this run
 
-        // ---- pass 2: pack.  acc holds bits not yet flushed; the first flushed word (head) may
-        // share its low bits with the previous run's tail, which arrives by shuffle afterwards.
-        uint32_t headWord = 0, headIdx = 0, tail = 0, tailIdx = 0;
-        if (active) {
-            unsigned long long acc = 0;
-            uint32_t accBits = p0 & 31, w = p0 >> 5;
-            bool first = true;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const uint32_t sym = (sy[j >> 2] >> ((j & 3) * 8)) & 0xFF;
-                const uint32_t e = sm.tab[sym * 32 + lane];
-                const uint32_t len = (uint32_t)(31 - __clz(e));
-                acc |= (unsigned long long)(e ^ (1u << len)) << accBits;
-                accBits += len;
-                if (accBits >= 32) {
-                    if (first) { headWord = (uint32_t)acc; headIdx = w; first = false; }
-                    else sm.stage[w] = (uint32_t)acc;
-                    w++; acc >>= 32; accBits -= 32;
-                }
+        if (!dense) {
+            // ---- pass 2: pack into the stage; head word = first flushed word of the run --------
+            uint32_t tail = 0, tailIdx = 0;
+            if (active) {
+                if (mode == 4) enc_pack_fast<4>(ent, p0, stageA, tail, tailIdx);
+                else if (mode == 2) enc_pack_fast<2>(ent, p0, stageA, tail, tailIdx);
+                else if (mode == 1) enc_pack_fast<1>(ent, p0, stageA, tail, tailIdx);
+                else enc_pack_generic(ent, p0, stageA, tail, tailIdx);
             }
-            tail = (uint32_t)acc; tailIdx = w;
+            // the tail of run t-1 lives in the low bits of the head word of run t
+            const uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+            if (lane == 31) sm.warpTail[warp] = tail;
+            if (active) {
+                if (lane > 0) sm.stage[p0 >> 5] |= prevTail;                 // own word, own earlier store
+                if ((uint32_t)tid == nRuns - 1) sm.stage[tailIdx] = tail;    // nobody follows: park the tail
+            }
+            __syncthreads();
+            if (active && lane == 0 && warp > 0) sm.stage[p0 >> 5] |= sm.warpTail[warp - 1];
+            __syncthreads();
+            // ---- copy out: whole words by plain coalesced stores, shared edge words by atomicOr ----
+            const uint32_t stageBits = r0 + fullBits;
+            const uint32_t nFull = stageBits >> 5, rem = stageBits & 31;
+            for (uint32_t j = tid; j < nFull; j += ENC_THREADS) {
+                if (j == 0 && r0) atomicOr(&out32[gw0], sm.stage[0]);
+                else out32[gw0 + j] = sm.stage[j];
+            }
+            if (tid == 0 && rem && nRuns) atomicOr(&out32[gw0 + nFull], sm.stage[nFull]);
+        } else if (active) {
+            // ---- dense chunk (> 16 bits per symbol on average; adversarial): straight to the container
+            unsigned long long bp = gw0 * 32 + p0;
+#pragma unroll 1
+            for (int j = 0; j < 32; j++) {
+                uint32_t e = 0;
+#pragma unroll
+                for (int q = 0; q < 32; q++) if (q == j) e = ent[q];
+                const uint32_t len = mode ? (e >> 24) : (uint32_t)(31 - __clz(e));
+                const uint32_t code = mode ? (e & 0xFFFFFFu) : (e ^ (1u << len));
+                const unsigned long long v = (unsigned long long)code << (bp & 31);
+                if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
+                if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
+                bp += len;
+            }
         }
-        // tail of lane l-1 lives in the low bits of lane l's head word
-        uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
-        if (lane == 31) sm.warpTail[warp] = tail;
-        if (active) {
-            if (lane > 0) headWord |= prevTail;
-            sm.stage[headIdx] = headWord;
-            if ((uint32_t)tid == nRuns - 1) sm.stage[tailIdx] = tail;   // nobody follows: park the tail
-        }
-        __syncthreads();
-        if (active && lane == 0 && warp > 0) sm.stage[headIdx] |= sm.warpTail[warp - 1];
-        __syncthreads();
-
-        // ---- copy out: whole words by plain coalesced stores, shared edge words by atomicOr ----
-        const uint32_t stageBits = r0 + fullBits;
-        const uint32_t nFull = stageBits >> 5, rem = stageBits & 31;
-        for (uint32_t j = tid; j < nFull; j += ENC_THREADS) {
-            if (j == 0 && r0) atomicOr(&out32[gw0], sm.stage[0]);
-            else out32[gw0 + j] = sm.stage[j];
-        }
-        if (tid == 0 && rem && nRuns) atomicOr(&out32[gw0 + nFull], sm.stage[nFull]);
         // ---- ragged end of the stream (< 32 symbols): serial append ---------------------------
         if (tid == 0 && cnt > nRuns * ENC_RUN) {
             unsigned long long bp = gb0 + fullBits;
             for (uint32_t i = nRuns * ENC_RUN; i < cnt; i++) {
                 const uint32_t e = sm.tab[(uint32_t)src[i] * 32];
-                const uint32_t len = (uint32_t)(31 - __clz(e));
-                const unsigned long long v = (unsigned long long)(e ^ (1u << len)) << (bp & 31);
-                atomicOr(&out32[bp >> 5], (uint32_t)v);
+                const uint32_t len = mode ? (e >> 24) : (uint32_t)(31 - __clz(e));
+                const uint32_t code = mode ? (e & 0xFFFFFFu) : (e ^ (1u << len));
+                const unsigned long long v = (unsigned long long)code << (bp & 31);
+                if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
                 if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
                 bp += len;
             }
@@ -551,10 +633,7 @@ k_headers(Ws ws, uint8_t *__restrict__ out, uint32_t nBlocks, uint32_t withHeade
 // =========================================================================================
 // launches
 // =========================================================================================
-void huff_init()
-{
-    cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
-}
+void huff_init() {}
 
 int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
                       uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
@@ -574,7 +653,7 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     k_seg_scan<<<(nSeg + 255) / 256, 256, 0, st>>>(ws, nSeg); launches++;
     k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, withHeader, outCap); launches++;
     if (mark) mark(markArg, 5);
-    k_encode<<<numSM * 3, ENC_THREADS, sizeof(EncSmem), st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
+    k_encode<<<numSM * 4, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
     if (mark) mark(markArg, 6);
     k_headers<<<(nBlocks + 3) / 4, 128, 0, st>>>(ws, out, nBlocks, withHeader, hdrTotalBytes, hdrBlocks, batchStartCursor);
     launches++;
