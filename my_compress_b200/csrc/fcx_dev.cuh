@@ -93,6 +93,11 @@ __device__ __forceinline__ uint32_t hash24(uint32_t gram, int bits)
     return ((gram & 0xFFFFFFu) * 2654435761u) >> (32 - bits);
 }
 
+__device__ __forceinline__ uint32_t hash32(uint32_t gram4, int bits)
+{
+    return (gram4 * 2654435761u) >> (32 - bits);
+}
+
 // byte-granular little-endian stores to arbitrarily aligned global memory
 __device__ __forceinline__ void st_u32_bytes(uint8_t *p, uint32_t v)
 {

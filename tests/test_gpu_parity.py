@@ -172,3 +172,16 @@ def test_round_trip_container():
         data = datagen.gen(family, nbytes, seed=5)
         blob = api.compress(data)
         assert api.decompress(blob) == data.tobytes()
+
+
+def test_multi_gpu_block_sharding_matches_single_gpu():
+    """fcx_compress_lz77 with a multi-device mask shards contiguous block ranges over the GPUs;
+    the container must not depend on the device count."""
+    ndev = api.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    data = datagen.gen("mixed", (9 << 20) + 777, seed=21)
+    one = api.compress(data, n_gpus=1)
+    for g in sorted({2, min(ndev, 4), ndev}):
+        assert api.compress(data, n_gpus=g) == one, "differs with %d GPUs" % g
+    assert one == _oracle_container(data)
