@@ -385,11 +385,11 @@ k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
 constexpr int ENC_THREADS = 256;
 constexpr int ENC_RUN = kChunkSyms / ENC_THREADS;     // 32 symbols per thread
 static_assert(ENC_RUN == 32, "run length is baked into the carry logic (>= 32 bits per run)");
-constexpr int ENC_STAGE_WORDS = 4064;                 // 16 bits per symbol on average; denser chunks take the slow path
+constexpr int ENC_STAGE_WORDS = 4060;                 // 16 bits per symbol on average; denser chunks take the slow path
 
 struct EncSmem {
     uint32_t tab[256 * 32];            // fast path: code | len<<24; generic path: code | 1<<len
-    uint32_t stage[ENC_STAGE_WORDS + 8];
+    alignas(16) uint32_t stage[ENC_STAGE_WORDS + 8];
     uint32_t warpBits[8];
     uint32_t warpTail[8];
 };
@@ -483,8 +483,10 @@ k_encode(Ws ws, uint32_t *__restrict__ out32)
         const uint32_t nRuns = cnt / ENC_RUN;
         const uint8_t *src = ws.strm[k] + (size_t)b * ws.strmStride[k] + (size_t)c * kChunkSyms;
         const unsigned long long gb0 = ws.segBitBase[s] + ws.chunkBitOff[chunk];
-        const uint32_t r0 = (uint32_t)(gb0 & 31);
-        const unsigned long long gw0 = gb0 >> 5;
+        // stage word k holds container word wBase + k; wBase is a multiple of 4, so 16-byte units
+        // line up on both sides and the copy-out can use 128-bit loads and stores
+        const uint32_t r0 = (uint32_t)(gb0 & 127);
+        const unsigned long long wBase = (gb0 >> 5) & ~3ull;
         const bool active = (uint32_t)tid < nRuns;
         const bool dense = r0 + ws.chunkBits[chunk] > (uint32_t)ENC_STAGE_WORDS * 32;   // does not fit the stage
 
@@ -543,17 +545,32 @@ k_encode(Ws ws, uint32_t *__restrict__ out32)
             __syncthreads();
             if (active && lane == 0 && warp > 0) sm.stage[p0 >> 5] |= sm.warpTail[warp - 1];
             __syncthreads();
-            // ---- copy out: whole words by plain coalesced stores, shared edge words by atomicOr ----
-            const uint32_t stageBits = r0 + fullBits;
-            const uint32_t nFull = stageBits >> 5, rem = stageBits & 31;
-            for (uint32_t j = tid; j < nFull; j += ENC_THREADS) {
-                if (j == 0 && r0) atomicOr(&out32[gw0], sm.stage[0]);
-                else out32[gw0 + j] = sm.stage[j];
+            // ---- copy out.  Words [first,last) are complete; `first` may share its low bits with the
+            // previous chunk / header bytes and `last` (if partial) its high bits with what follows:
+            // those two are merged with atomicOr, whole 16-byte units go out as 128-bit stores.
+            const uint32_t first = r0 >> 5, fbit = r0 & 31;
+            const uint32_t endBit = r0 + fullBits, last = endBit >> 5, rem = endBit & 31;
+            uint32_t *dst = out32 + wBase;
+            const uint32_t vBeg = (first + (fbit ? 1u : 0u) + 3u) >> 2, vEnd = last >> 2;
+            if (vBeg < vEnd) {
+                for (uint32_t v = vBeg + tid; v < vEnd; v += ENC_THREADS)
+                    reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(sm.stage)[v];
+                if (tid < 8) {                                                   // scalar edges
+                    const uint32_t k = tid < 4 ? first + tid : 4 * vEnd + (tid - 4);
+                    const bool inHead = tid < 4 && k < 4 * vBeg, inTail = tid >= 4 && k < last;
+                    if (inHead || inTail) {
+                        if (k == first && fbit) atomicOr(&dst[k], sm.stage[k]); else dst[k] = sm.stage[k];
+                    }
+                }
+            } else {
+                for (uint32_t k = first + tid; k < last; k += ENC_THREADS) {
+                    if (k == first && fbit) atomicOr(&dst[k], sm.stage[k]); else dst[k] = sm.stage[k];
+                }
             }
-            if (tid == 0 && rem && nRuns) atomicOr(&out32[gw0 + nFull], sm.stage[nFull]);
+            if (tid == 0 && rem && nRuns) atomicOr(&dst[last], sm.stage[last]);
         } else if (active) {
             // ---- dense chunk (> 16 bits per symbol on average; adversarial): straight to the container
-            unsigned long long bp = gw0 * 32 + p0;
+            unsigned long long bp = wBase * 32 + p0;
 #pragma unroll 1
             for (int j = 0; j < 32; j++) {
                 uint32_t e = 0;
@@ -580,7 +597,8 @@ k_encode(Ws ws, uint32_t *__restrict__ out32)
                 bp += len;
             }
         }
-        __syncthreads();
+        // no barrier here: the scan barrier of the next chunk orders this copy-out before the next
+        // pack, and warpBits / warpTail are rewritten only after barriers every thread has passed
     }
 }
 
