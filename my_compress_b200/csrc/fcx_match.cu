@@ -209,7 +209,16 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
     }
 
     // ---- per-position walk ----------------------------------------------------------------
+    // One flat loop over the chains of all overlapping sub-regions.  A visit loads the
+    // candidate's first eight bytes and tests them against a register copy of the position's
+    // own eight bytes under a mask covering bytes 0..bestL: a candidate that fails cannot beat
+    // the current best and costs ~20 straight-line instructions; only a candidate that passes
+    // (a strict improvement, a handful per position) gets its exact length computed, and only
+    // matches of eight bytes or more enter the extension loop.  Lanes therefore stay in lockstep
+    // for almost every visit.
     const size_t outBase = (size_t)b * kBlockBytes;
+    uint32_t xsB = xsA, headB = headA, upB = upA;            // opaque copies: keep the bases in registers
+    asm volatile("" : "+r"(xsB), "+r"(headB), "+r"(upB));
     const uint32_t orderA = smem_addr(sm.order);
     for (int k = 0; k < MT_PER_THREAD; k++) {
         const int idx = k * MT_THREADS + tid;
@@ -219,22 +228,43 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         const int cap = min(kMaxLen, n - 1 - i);
         int bestL = kMinLen - 1, bestS = 0;
         if (i > 0 && cap >= kMinLen) {
-            const uint32_t h = hash24(lds_u32_unaligned(xsA + si), MT_HBITS);
+            const uint32_t xi = xsB + si;
+            const uint32_t wsi0 = lds_u32_unaligned(xi), wsi1 = lds_u32_unaligned(xi + 4);
+            const uint32_t h = hash24(wsi0, MT_HBITS);
             const int lo = max(si - kWindow, minSlot);
-            const uint32_t xi = xsA + si;
-            bool done = false;
-            for (int sr = lo >> 10; sr <= (si >> 10) && !done; sr++) {
-                int s = (int)(lds_u32(headA + 4 * (sr * MT_HB + h)) & 0xFFFF);
-                while (s != (int)MT_NONE && s < si) {
-                    const int cur = s;
-                    s = (int)lds_u16(upA + 2 * cur);
-                    if (cur >= lo && lds_u8(xsA + cur + bestL) == lds_u8(xi + bestL)) {
-                        const int L = lcp_capped(xsA, cur, si, cap);
-                        if (L > bestL) {
-                            bestL = L; bestS = cur;
-                            if (L == cap) { done = true; break; }   // nothing nearer can beat the cap
-                        }
-                    }
+            const int srLast = si >> 10;
+            int sr = lo >> 10;
+            uint32_t hp = headB + 4 * (sr * MT_HB + h);
+            int s = (int)(lds_u32(hp) & 0xFFFF);
+            while (s < lo) s = (int)lds_u16(upB + 2 * s);           // entries before the window (MT_NONE = 0xFFFF ends it)
+            uint32_t mLo = 0x00FFFFFFu, mHi = 0u;                   // bytes 0..bestL must agree to beat bestL
+            for (;;) {
+                if (s >= si) {                                      // chain exhausted (MT_NONE >= si as well)
+                    if (sr >= srLast) break;
+                    sr++; hp += 4 * MT_HB;
+                    s = (int)(lds_u32(hp) & 0xFFFF);
+                    continue;
+                }
+                const int cur = s;
+                s = (int)lds_u16(upB + 2 * cur);
+                const uint32_t a = xsB + cur, al = a & ~3u, sh = (a & 3u) * 8;
+                const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4), w2 = lds_u32(al + 8);
+                const uint32_t d0 = __funnelshift_r(w0, w1, sh) ^ wsi0;
+                const uint32_t d1 = __funnelshift_r(w1, w2, sh) ^ wsi1;
+                if ((d0 & mLo) | (d1 & mHi)) continue;              // cannot beat the current best
+                // strict improvement (or, once bestL >= 8, a candidate agreeing on all eight bytes)
+                int m = d0 ? ((__ffs(d0) - 1) >> 3) : (d1 ? 4 + ((__ffs(d1) - 1) >> 3) : 8);
+                if (m == 8 && cap > 8) {
+                    if (bestL > 8 && lds_u8(a + bestL) != lds_u8(xi + bestL)) continue;
+                    m = 8 + lcp_capped(xsB, cur + 8, si + 8, cap - 8);
+                }
+                m = min(m, cap);
+                if (m > bestL) {
+                    bestL = m; bestS = cur;
+                    if (m == cap) break;                            // nothing nearer can beat the cap
+                    const int nb = 8 * (m + 1);                     // mask now covers bytes 0..m
+                    mLo = nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+                    mHi = nb >= 64 ? 0xFFFFFFFFu : (nb > 32 ? ((1u << (nb - 32)) - 1u) : 0u);
                 }
             }
         }
