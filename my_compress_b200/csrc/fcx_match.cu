@@ -38,7 +38,7 @@ constexpr int MT_THREADS = 256;
 constexpr int MT_PER_THREAD = MT_TILE / MT_THREADS;   // 16
 constexpr uint32_t MT_NONE = 0xFFFF;
 constexpr int MT_BINS = 32;
-constexpr uint32_t MT_SORT_THRESHOLD = 6;        // sort only when some bucket holds more than this
+constexpr uint32_t MT_SORT_THRESHOLD = 12;       // sort only when some bucket holds more than this
 
 struct MatchSmem {
     uint32_t xs[(MT_REGION + MT_LOOK) / 4];
@@ -50,6 +50,11 @@ struct MatchSmem {
     uint32_t binStart[MT_BINS];
     uint32_t maxPop;
 };
+
+// byte masks: entry m covers bytes 0..m of an 8-byte little-endian window (m >= 7: all eight)
+__constant__ unsigned long long c_byteMask[9] = {
+    0xFFull, 0xFFFFull, 0xFFFFFFull, 0xFFFFFFFFull, 0xFFFFFFFFFFull, 0xFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFull,
+    0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull};
 
 // ---- explicit shared-memory loads (32-bit shared addresses held in registers) -------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -233,16 +238,18 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const uint32_t h = hash24(wsi0, MT_HBITS);
             const int lo = max(si - kWindow, minSlot);
             const int srLast = si >> 10;
-            int sr = lo >> 10;
-            uint32_t hp = headB + 4 * (sr * MT_HB + h);
+            const int sr0 = lo >> 10;
+            // heads of the (at most three) chains to walk, loaded up front; -1 = no further chain
+            const uint32_t hp = headB + 4 * (sr0 * MT_HB + h);
             int s = (int)(lds_u32(hp) & 0xFFFF);
+            int next1 = sr0 + 1 <= srLast ? (int)(lds_u32(hp + 4 * MT_HB) & 0xFFFF) : -1;
+            int next2 = sr0 + 2 <= srLast ? (int)(lds_u32(hp + 8 * MT_HB) & 0xFFFF) : -1;
             while (s < lo) s = (int)lds_u16(upB + 2 * s);           // entries before the window (MT_NONE = 0xFFFF ends it)
             uint32_t mLo = 0x00FFFFFFu, mHi = 0u;                   // bytes 0..bestL must agree to beat bestL
             for (;;) {
                 if (s >= si) {                                      // chain exhausted (MT_NONE >= si as well)
-                    if (sr >= srLast) break;
-                    sr++; hp += 4 * MT_HB;
-                    s = (int)(lds_u32(hp) & 0xFFFF);
+                    if (next1 < 0) break;
+                    s = next1; next1 = next2; next2 = -1;
                     continue;
                 }
                 const int cur = s;
@@ -253,7 +260,8 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
                 const uint32_t d1 = __funnelshift_r(w1, w2, sh) ^ wsi1;
                 if ((d0 & mLo) | (d1 & mHi)) continue;              // cannot beat the current best
                 // strict improvement (or, once bestL >= 8, a candidate agreeing on all eight bytes)
-                int m = d0 ? ((__ffs(d0) - 1) >> 3) : (d1 ? 4 + ((__ffs(d1) - 1) >> 3) : 8);
+                const unsigned long long d = ((unsigned long long)d1 << 32) | d0;
+                int m = d ? ((__ffsll((long long)d) - 1) >> 3) : 8;
                 if (m == 8 && cap > 8) {
                     if (bestL > 8 && lds_u8(a + bestL) != lds_u8(xi + bestL)) continue;
                     m = 8 + lcp_capped(xsB, cur + 8, si + 8, cap - 8);
@@ -262,9 +270,8 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
                 if (m > bestL) {
                     bestL = m; bestS = cur;
                     if (m == cap) break;                            // nothing nearer can beat the cap
-                    const int nb = 8 * (m + 1);                     // mask now covers bytes 0..m
-                    mLo = nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u);
-                    mHi = nb >= 64 ? 0xFFFFFFFFu : (nb > 32 ? ((1u << (nb - 32)) - 1u) : 0u);
+                    const unsigned long long mk = c_byteMask[min(m, 8)];   // now bytes 0..m must agree
+                    mLo = (uint32_t)mk; mHi = (uint32_t)(mk >> 32);
                 }
             }
         }
