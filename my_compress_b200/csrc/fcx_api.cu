@@ -24,6 +24,7 @@ void launch_match(const uint8_t *in, const uint32_t *blkLen, uint8_t *lenCode, u
 void match_init();
 // fcx_parse.cu
 int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32_t nBlocks, uint32_t maxLen, cudaStream_t st);
+void parse_init();
 // fcx_huff.cu
 void huff_init();
 int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
@@ -160,6 +161,7 @@ extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks
     cudaMemset(w.totals, 0, TOT_WORDS * sizeof(uint32_t));
     cudaMemset(w.counters, 0, C_WORDS * sizeof(uint64_t));
     match_init();
+    parse_init();
     huff_init();
     CK(cudaGetLastError());
     *out = c;

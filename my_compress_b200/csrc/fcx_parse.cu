@@ -118,19 +118,30 @@ k_parse_exits(const uint32_t *__restrict__ blkLen, const uint8_t *__restrict__ l
 }
 
 // ---- 2: compose them along each block -----------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_parse_entries(const uint32_t *__restrict__ blkLen, Ws ws, uint32_t nBlocks)
+// The composition is a chain of 256 dependent look-ups.  Out of global memory that is 256
+// exposed L2 latencies per block, so the CTA first pulls the block's whole exit table (129 KiB)
+// into shared memory with coalesced 16-byte loads and thread 0 then hops through it there.
+constexpr int PE_THREADS = 512;
+constexpr int PE_TABLE = kParseTilesPerBlock * PT_ENTRIES;     // 66048 entries
+__global__ void __launch_bounds__(PE_THREADS)
+k_parse_entries(const uint32_t *__restrict__ blkLen, Ws ws)
 {
-    const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (b >= nBlocks || (threadIdx.x & 31)) return;
+    extern __shared__ __align__(16) uint16_t exS[];
+    const uint32_t b = blockIdx.x;
     const int n = (int)blkLen[b];
     const int nTiles = (n + PT - 1) / PT;
-    const uint16_t *ex = ws.parseExit + (size_t)b * kParseTilesPerBlock * PT_ENTRIES;
-    uint16_t *en = ws.tileEntry + (size_t)b * kParseTilesPerBlock;
-    uint32_t e = 0;
-    for (int t = 0; t < nTiles; t++) {
-        en[t] = (uint16_t)e;
-        e = ex[(size_t)t * PT_ENTRIES + e];
+    const uint16_t *ex = ws.parseExit + (size_t)b * PE_TABLE;
+    const int nVec = (nTiles * PT_ENTRIES * 2 + 15) / 16;       // table rows are 516 bytes: the block's table is contiguous
+    for (int v = threadIdx.x; v < nVec; v += PE_THREADS)
+        reinterpret_cast<uint4 *>(exS)[v] = reinterpret_cast<const uint4 *>(ex)[v];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint16_t *en = ws.tileEntry + (size_t)b * kParseTilesPerBlock;
+        uint32_t e = 0;
+        for (int t = 0; t < nTiles; t++) {
+            en[t] = (uint16_t)e;
+            e = exS[t * PT_ENTRIES + e];
+        }
     }
 }
 
@@ -218,7 +229,6 @@ k_parse_scan(const uint32_t *__restrict__ blkLen, Ws ws)
 struct EmitSmem {
     JumpSmem j;
     uint32_t xs[(PT + PT_LOOK) / 4];
-    uint16_t ds[PT];
     uint8_t cbuf[PT + 16];
     uint32_t fbits[PT / 32 + 4];
     uint32_t pbits[368];
@@ -260,9 +270,8 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     const int limit = min(PT, n - tb);
     const uint8_t *x = in + (size_t)b * kBlockBytes;
     const uint16_t *dsG = dist + (size_t)b * kBlockBytes;
-    // stage distances, bytes (+ look-ahead for c = x[i+len]) and zero the bit buffers
-    reinterpret_cast<uint4 *>(sm.ds)[tid] = reinterpret_cast<const uint4 *>(dsG + tb)[tid];
-    reinterpret_cast<uint4 *>(sm.ds)[tid + 256] = reinterpret_cast<const uint4 *>(dsG + tb)[tid + 256];
+    // stage bytes (+ look-ahead for c = x[i+len]) and zero the bit buffers; distances are read
+    // straight from global memory, only for the tokens that are matches
     for (int v = tid; v < (PT + PT_LOOK) / 16; v += PT_THREADS) {
         const int pos = tb + v * 16;
         uint4 q;
@@ -311,23 +320,39 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
 
     const uint4 bases = ws.tileCnt[(size_t)b * kParseTilesPerBlock + tile];      // exclusive tok / mat / gbit ranks
     const uint32_t fOff = bases.x & 31, pOff = (kPBits * bases.y) & 31, gOffBits = bases.z & 31;
+    // A thread's tokens have consecutive ranks, so its flag bits (<= 16) and packed distances
+    // (<= 5 x 11 bits) are contiguous: gather them in registers and merge once, instead of one
+    // shared-memory atomic per token.
+    const uint32_t tok0 = tokIdx, mat0 = matIdx;
+    uint32_t flagReg = 0;
+    unsigned long long pReg = 0;
     for (int e = e0; e < hi;) {
         const int len = code_len(lcb[e]);
         sm.cbuf[tokIdx] = xsb[e + len];                                           // mc:1489: byte after the match
         if (len == 0) {
-            or_bits(sm.fbits, fOff + tokIdx, 1u, 1);                              // mc:2087-2089: bit set = literal
+            flagReg |= 1u << (tokIdx - tok0);                                     // mc:2087-2089: bit set = literal
         } else {
-            or_bits(sm.pbits, pOff + kPBits * matIdx, sm.ds[e], kPBits);          // mc:1301-1309
+            pReg |= (unsigned long long)dsG[tb + e] << (kPBits * (matIdx - mat0));  // mc:1301-1309
             const uint32_t gp = gOffBits + gOff;
             const int q = len >> 2;                                               // mc:267-269: q ones, 0, 2 remainder bits
-            if (q > 32) { or_bits(sm.gbits, gp, 0xFFFFFFFFu, 32); or_bits(sm.gbits, gp + 32, 0xFFFFFFFFu >> (64 - q), q - 32); }
-            else if (q > 0) or_bits(sm.gbits, gp, 0xFFFFFFFFu >> (32 - q), q);
-            or_bits(sm.gbits, gp + q + 1, (uint32_t)(len & 3), 2);
+            if (q <= 29) {                                                        // whole code fits 32 bits
+                or_bits(sm.gbits, gp, ((1u << q) - 1u) | ((uint32_t)(len & 3) << (q + 1)), q + 3);
+            } else {
+                if (q > 32) { or_bits(sm.gbits, gp, 0xFFFFFFFFu, 32); or_bits(sm.gbits, gp + 32, 0xFFFFFFFFu >> (64 - q), q - 32); }
+                else or_bits(sm.gbits, gp, 0xFFFFFFFFu >> (32 - q), q);
+                or_bits(sm.gbits, gp + q + 1, (uint32_t)(len & 3), 2);
+            }
             matIdx++;
             gOff += (uint32_t)q + 3;
         }
         tokIdx++;
         e += len + 1;
+    }
+    if (flagReg) or_bits(sm.fbits, fOff + tok0, flagReg, 16);
+    if (matIdx > mat0) {
+        const uint32_t pp = pOff + kPBits * mat0;
+        or_bits(sm.pbits, pp, (uint32_t)pReg, 32);
+        if (matIdx - mat0 > 2) or_bits(sm.pbits, pp + 32, (uint32_t)(pReg >> 32), 32);
     }
     __syncthreads();
     uint8_t *cOut = ws.strm[1] + (size_t)b * ws.strmStride[1] + bases.x;
@@ -336,6 +361,11 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     flush_bits(reinterpret_cast<uint32_t *>(ws.strm[2] + (size_t)b * ws.strmStride[2]), sm.pbits,
                (unsigned long long)kPBits * bases.y, kPBits * tileMat);
     flush_bits(reinterpret_cast<uint32_t *>(ws.strm[3] + (size_t)b * ws.strmStride[3]), sm.gbits, bases.z, tileG);
+}
+
+void parse_init()
+{
+    cudaFuncSetAttribute(k_parse_entries, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PE_TABLE * sizeof(uint16_t) + 16));
 }
 
 int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32_t nBlocks, uint32_t maxLen, cudaStream_t st)
@@ -347,7 +377,7 @@ int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32
     cudaMemsetAsync(ws.strm[2], 0, (size_t)nBlocks * ws.strmStride[2], st);
     cudaMemsetAsync(ws.strm[3], 0, (size_t)nBlocks * ws.strmStride[3], st);
     k_parse_exits<<<grid, PT_THREADS, 0, st>>>(blkLen, ws.lenCode, ws);
-    k_parse_entries<<<(nBlocks + 3) / 4, 128, 0, st>>>(blkLen, ws, nBlocks);
+    k_parse_entries<<<nBlocks, PE_THREADS, PE_TABLE * sizeof(uint16_t) + 16, st>>>(blkLen, ws);
     k_parse_count<<<grid, PT_THREADS, 0, st>>>(blkLen, ws.lenCode, ws);
     k_parse_scan<<<nBlocks, kParseTilesPerBlock, 0, st>>>(blkLen, ws);
     k_parse_emit<<<grid, PT_THREADS, 0, st>>>(in, blkLen, ws.lenCode, ws.dist, ws);
