@@ -106,8 +106,12 @@ int fcx_ctx_stage_times(fcx_ctx *ctx, const char **names, float *ms, int cap);
 
 /* ---- stage-level probes (device pointers; used by tests/ to localise parity) -------- */
 
-/* per-position longest match of one block (mc:1446-1514): len[i] in {0,3..257}, dist[i]. */
+/* per-position longest match of one block (mc:1446-1514): len[i] in {0,3..257}, dist[i].
+ * fcx_probe_match evaluates EVERY position; fcx_probe_match_auto runs the kernel as the product
+ * path does, where a tile of long matches only evaluates the positions a parse can reach
+ * (every position on the parse chain is exact, unreachable ones read 0). */
 int fcx_probe_match(fcx_ctx *ctx, const uint8_t *d_in, uint32_t n, uint16_t *d_len, uint16_t *d_dist);
+int fcx_probe_match_auto(fcx_ctx *ctx, const uint8_t *d_in, uint32_t n, uint16_t *d_len, uint16_t *d_dist);
 /* greedy parse + stream split of one block (mc:1675-1714, 2073-2113, 2150-2161, 1292-1313,
  * 258-304): host outputs.  streams: bitmap bytes, c bytes, packed-p bytes, Golomb bytes. */
 int fcx_probe_streams(fcx_ctx *ctx, const uint8_t *d_in, uint32_t n, uint32_t *T, uint32_t *Pc, uint32_t *G,

@@ -34,7 +34,7 @@ EXPORTS = [
     "fcx_last_error", "fcx_device_count", "fcx_compress_bound", "fcx_compress_block_lz77", "fcx_compress_lz77",
     "fcx_decompress_block_lz77", "fcx_decompress_lz77", "fcx_ctx_create", "fcx_ctx_destroy", "fcx_ctx_set_stream",
     "fcx_compress_lz77_device", "fcx_ctx_finish", "fcx_ctx_launch_count", "fcx_ctx_stats", "fcx_ctx_enable_timing",
-    "fcx_ctx_stage_times", "fcx_probe_match", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
+    "fcx_ctx_stage_times", "fcx_probe_match", "fcx_probe_match_auto", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
 ]
 
 
@@ -67,6 +67,7 @@ def lib():
     L.fcx_ctx_enable_timing.argtypes = [C.c_void_p, C.c_int]
     L.fcx_ctx_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.fcx_probe_match.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.fcx_probe_match_auto.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fcx_probe_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.fcx_probe_huffman_section.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
@@ -218,12 +219,14 @@ class DeviceCompressor:
         return {names[i].decode(): float(ms[i]) for i in range(k)}
 
     # ---- stage probes (tests) --------------------------------------------------------------
-    def probe_match(self, d_in):
+    def probe_match(self, d_in, auto=False):
+        """auto=False: every position evaluated; auto=True: as the product path runs it (lazy tiles)."""
         t = self.torch
         n = d_in.numel()
         ln = t.empty(n, dtype=t.int16, device=d_in.device)
         ds = t.empty(n, dtype=t.int16, device=d_in.device)
-        _check(lib().fcx_probe_match(self._ctx, C.c_void_p(d_in.data_ptr()), n, C.c_void_p(ln.data_ptr()), C.c_void_p(ds.data_ptr())))
+        fn = lib().fcx_probe_match_auto if auto else lib().fcx_probe_match
+        _check(fn(self._ctx, C.c_void_p(d_in.data_ptr()), n, C.c_void_p(ln.data_ptr()), C.c_void_p(ds.data_ptr())))
         return (ln.cpu().numpy().view(np.uint16).astype(np.uint32), ds.cpu().numpy().view(np.uint16).astype(np.uint32))
 
     def probe_streams(self, d_in):

@@ -20,7 +20,7 @@
 namespace fcx {
 // fcx_match.cu
 void launch_match(const uint8_t *in, const uint32_t *blkLen, uint8_t *lenCode, uint16_t *dist, uint32_t nBlocks,
-                  uint32_t maxLen, cudaStream_t st);
+                  uint32_t maxLen, bool forceEager, cudaStream_t st);
 void match_init();
 // fcx_parse.cu
 int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32_t nBlocks, uint32_t maxLen, cudaStream_t st);
@@ -267,7 +267,7 @@ static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_o
         const uint32_t withHeader = (first == 0 && (flags & FCX_WITH_HEADER)) ? 1u : 0u;
         mark_stage(c, -1);
         k_set_blklen<<<(nb + 255) / 256, 256, 0, st>>>(w.blkLen, n, (uint32_t)first, nb);
-        launch_match(bin, w.blkLen, w.lenCode, w.dist, nb, maxLen, st);
+        launch_match(bin, w.blkLen, w.lenCode, w.dist, nb, maxLen, false, st);
         mark_stage(c, ST_MATCH);
         c->launches += 2 + launch_parse(bin, w.blkLen, w, nb, maxLen, st);
         mark_stage(c, ST_PARSE);
@@ -535,13 +535,25 @@ __global__ void k_expand_len(const uint8_t *lenCode, uint16_t *len, uint32_t n)
     if (i < n) len[i] = lenCode[i] ? (uint16_t)(lenCode[i] + 2) : (uint16_t)0;
 }
 
+static int probe_match(fcx_ctx *c, const uint8_t *d_in, uint32_t n, uint16_t *d_len, uint16_t *d_dist, bool eager);
+
 extern "C" int fcx_probe_match(fcx_ctx *c, const uint8_t *d_in, uint32_t n, uint16_t *d_len, uint16_t *d_dist)
+{
+    return probe_match(c, d_in, n, d_len, d_dist, true);
+}
+
+extern "C" int fcx_probe_match_auto(fcx_ctx *c, const uint8_t *d_in, uint32_t n, uint16_t *d_len, uint16_t *d_dist)
+{
+    return probe_match(c, d_in, n, d_len, d_dist, false);
+}
+
+static int probe_match(fcx_ctx *c, const uint8_t *d_in, uint32_t n, uint16_t *d_len, uint16_t *d_dist, bool eager)
 {
     if (!c || !d_in || !d_len || !d_dist || n == 0 || n > kBlockBytes) return fail(FCX_ERR_ARG, "bad arguments");
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     k_set_blklen<<<1, 256, 0, st>>>(c->ws.blkLen, n, 0, 1);
-    launch_match(d_in, c->ws.blkLen, c->ws.lenCode, c->ws.dist, 1, n, st);
+    launch_match(d_in, c->ws.blkLen, c->ws.lenCode, c->ws.dist, 1, n, eager, st);
     k_expand_len<<<(n + 255) / 256, 256, 0, st>>>(c->ws.lenCode, d_len, n);
     CK(cudaMemcpyAsync(d_dist, c->ws.dist, (size_t)n * 2, cudaMemcpyDeviceToDevice, st));
     c->launches += 3;
@@ -557,7 +569,7 @@ extern "C" int fcx_probe_streams(fcx_ctx *c, const uint8_t *d_in, uint32_t n, ui
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     k_set_blklen<<<1, 256, 0, st>>>(c->ws.blkLen, n, 0, 1);
-    launch_match(d_in, c->ws.blkLen, c->ws.lenCode, c->ws.dist, 1, n, st);
+    launch_match(d_in, c->ws.blkLen, c->ws.lenCode, c->ws.dist, 1, n, false, st);
     c->launches += 2 + launch_parse(d_in, c->ws.blkLen, c->ws, 1, n, st);
     uint32_t m[M_WORDS];
     CK(cudaMemcpyAsync(m, c->ws.meta, sizeof(m), cudaMemcpyDeviceToHost, st));

@@ -22,6 +22,14 @@
 // busy.  So when a tile has long chains its positions are first counting-sorted by estimated
 // chain length (bucket populations, half-octave bins, heaviest first) and lanes take
 // consecutive entries of that order: neighbouring lanes then walk chains of similar length.
+// Long-match tiles are handled lazily.  A 64-position probe measures the mean match length;
+// when it is large, almost every position lies inside a match of an earlier position and will
+// never be a parse cursor.  The parse can only enter a tile at offsets 0..257, so such a tile
+// evaluates exactly those 258 positions plus a speculative chain start every 64 positions, and
+// follows next(p) = p + len + 1 from each until it lands on a position that is already
+// evaluated (chains merge after a token or two).  The evaluated set then contains every
+// possible entry and is closed under next(), so whatever the true entry turns out to be, the
+// parse only ever visits evaluated positions; all others keep a literal placeholder.
 #include "fcx_dev.cuh"
 
 namespace fcx {
@@ -36,19 +44,23 @@ constexpr int MT_HB = 1 << MT_HBITS;             // buckets per sub-region
 constexpr int MT_LOOK = 272;                     // >= 257 + 8
 constexpr int MT_THREADS = 256;
 constexpr int MT_PER_THREAD = MT_TILE / MT_THREADS;   // 16
+constexpr int MT_PROBES = 64;                         // positions sampled per tile
+constexpr int MT_LONG_MEAN = 12;                      // mean probed match length that switches a tile to lazy evaluation
+constexpr int MT_SPEC_STRIDE = 64;                    // lazy mode: a speculative chain starts every 64 positions
 constexpr uint32_t MT_NONE = 0xFFFF;
 constexpr int MT_BINS = 32;
 constexpr uint32_t MT_SORT_THRESHOLD = 12;       // sort only when some bucket holds more than this
 
 struct MatchSmem {
     uint32_t xs[(MT_REGION + MT_LOOK) / 4];
-    uint32_t head[MT_NSUB * MT_HB];              // low 16: lowest slot (0xFFFF none), high 16: population
+    uint16_t head[MT_NSUB * MT_HB];              // lowest slot of the bucket (0xFFFF none)
     uint16_t up[MT_REGION];
     uint16_t order[MT_TILE];
-    uint8_t bin[MT_TILE];
+    uint8_t pop[MT_NSUB * MT_HB / 2];            // population of bucket pairs (h>>1), saturating at 255: work estimate only
     uint32_t binCount[MT_BINS];
     uint32_t binStart[MT_BINS];
     uint32_t maxPop;
+    uint32_t probeSum;
 };
 
 // byte masks: entry m covers bytes 0..m of an 8-byte little-endian window (m >= 7: all eight)
@@ -97,9 +109,175 @@ __device__ __forceinline__ int lcp_capped(uint32_t xsA, int a, int b, int cap)
     return cap;
 }
 
+// Longest match of the position at slot si (see the kernel comment for the walk).
+struct MatchCtx {
+    uint32_t xsB, headB, upB, popB;
+    int minSlot;
+};
+
+__device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, int &bestLOut, int &bestSOut)
+{
+    const uint32_t xsB = c.xsB, upB = c.upB;
+    int bestL = kMinLen - 1, bestS = 0;
+    const uint32_t xi = xsB + si;
+    const uint32_t wsi0 = lds_u32_unaligned(xi), wsi1 = lds_u32_unaligned(xi + 4);
+    const uint32_t h = hash24(wsi0, MT_HBITS);
+    const int lo = max(si - kWindow, c.minSlot);
+    const int srLast = si >> 10;
+    const int sr0 = lo >> 10;
+    uint32_t mLo = 0x00FFFFFFu, mHi = 0u;               // bytes 0..bestL must agree to beat bestL
+    // heads of the (at most three) chains to walk, loaded up front; -1 = no further chain
+    const uint32_t hp = c.headB + 2 * (sr0 * MT_HB + h);
+    int s = (int)lds_u16(hp);
+    int next1 = sr0 + 1 <= srLast ? (int)lds_u16(hp + 2 * MT_HB) : -1;
+    int next2 = sr0 + 2 <= srLast ? (int)lds_u16(hp + 4 * MT_HB) : -1;
+    while (s < lo) s = (int)lds_u16(upB + 2 * s);       // entries before the window (MT_NONE = 0xFFFF ends it)
+    for (;;) {
+        if (s >= si) {                                  // chain exhausted (MT_NONE >= si as well)
+            if (next1 < 0) break;
+            s = next1; next1 = next2; next2 = -1;
+            continue;
+        }
+        const int cur = s;
+        s = (int)lds_u16(upB + 2 * cur);
+        const uint32_t a = xsB + cur, al = a & ~3u, sh = (a & 3u) * 8;
+        const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4), w2 = lds_u32(al + 8);
+        const uint32_t d0 = __funnelshift_r(w0, w1, sh) ^ wsi0;
+        const uint32_t d1 = __funnelshift_r(w1, w2, sh) ^ wsi1;
+        if ((d0 & mLo) | (d1 & mHi)) continue;          // cannot beat the current best
+        // strict improvement (or, once bestL >= 7, a candidate agreeing on all eight bytes)
+        const unsigned long long d = ((unsigned long long)d1 << 32) | d0;
+        int m = d ? ((__ffsll((long long)d) - 1) >> 3) : 8;
+        if (m == 8 && cap > 8) {
+            if (bestL > 8 && lds_u8(a + bestL) != lds_u8(xi + bestL)) continue;
+            m = 8 + lcp_capped(xsB, cur + 8, si + 8, cap - 8);
+        }
+        m = min(m, cap);
+        if (m > bestL) {
+            bestL = m; bestS = cur;
+            if (m == cap) break;                        // nothing nearer can beat the cap
+            const unsigned long long mk = c_byteMask[min(m, 8)];   // now bytes 0..m must agree
+            mLo = (uint32_t)mk; mHi = (uint32_t)(mk >> 32);
+        }
+    }
+    bestLOut = bestL; bestSOut = bestS;
+}
+
+// eager mode: every position of the tile, one per lane per trip, in work-sorted order
+__device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &ctx, bool sorted, int tileSlots,
+                                                 int regionBase, int n, size_t outBase,
+                                                 uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t xsA = ctx.xsB;
+    const int minSlot = ctx.minSlot;
+    // ---- balance: counting sort of the positions by estimated chain length -----------------------
+    if (sorted) {
+        // half-octave bin of a position's estimated chain length (sum of bucket populations)
+        auto pos_bin = [&](int idx) -> uint32_t {
+            const int si = MT_HALO + idx;
+            const uint32_t h = hash24(lds_u32_unaligned(xsA + si), MT_HBITS);
+            const int lo = max(si - kWindow, minSlot);
+            uint32_t est = 0;
+            for (int sr = lo >> 10; sr <= (si >> 10); sr++) est += lds_u8(ctx.popB + sr * (MT_HB / 2) + (h >> 1));
+            if (!est) return 0u;
+            const int msb = 31 - __clz(est);
+            const int half = msb > 0 ? (int)((est >> (msb - 1)) & 1u) : 0;
+            return (uint32_t)min(MT_BINS - 1, 1 + 2 * msb + half);
+        };
+        for (int k = 0; k < MT_PER_THREAD; k++) {
+            const int idx = k * MT_THREADS + tid;
+            const uint32_t bn = idx < tileSlots ? pos_bin(idx) : 0xFFu;
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
+            if (bn != 0xFF && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&sm.binCount[bn], (uint32_t)__popc(grp));
+        }
+        __syncthreads();
+        if (tid == 0) {                                    // heaviest bin first
+            uint32_t acc = 0;
+            for (int bn = MT_BINS - 1; bn >= 0; bn--) { sm.binStart[bn] = acc; acc += sm.binCount[bn]; }
+        }
+        __syncthreads();
+        for (int k = 0; k < MT_PER_THREAD; k++) {
+            const int idx = k * MT_THREADS + tid;
+            const uint32_t bn = idx < tileSlots ? pos_bin(idx) : 0xFFu;   // recomputed: cheaper than 4 KB of shared memory
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
+            const int leader = __ffs(grp) - 1;
+            uint32_t base = 0;
+            if (bn != 0xFF && lane == leader) base = atomicAdd(&sm.binStart[bn], (uint32_t)__popc(grp));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (bn != 0xFF) sm.order[base + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)idx;
+        }
+        __syncthreads();
+    }
+    const uint32_t orderA = smem_addr(sm.order);
+    for (int k = 0; k < MT_PER_THREAD; k++) {
+        const int idx = k * MT_THREADS + tid;
+        if (idx >= tileSlots) break;
+        const int p = sorted ? (int)lds_u16(orderA + 2 * idx) : idx;
+        const int si = MT_HALO + p;
+        const int i = regionBase + si;
+        const int cap = min(kMaxLen, n - 1 - i);
+        int bestL = 0, bestS = 0;
+        if (i > 0 && cap >= kMinLen) match_one(ctx, si, cap, bestL, bestS);
+        const bool hit = bestL >= kMinLen;
+        lenCode[outBase + i] = hit ? (uint8_t)(bestL - 2) : (uint8_t)0;
+        dist[outBase + i] = hit ? (uint16_t)(si - bestS) : (uint16_t)0;
+    }
+}
+
+// lazy mode (long-match tiles): evaluate the 258 possible parse entries and a speculative start
+// every 64 positions, then follow every chain until it lands on an evaluated position
+__device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &ctx, int tileSlots,
+                                                int regionBase, int n, size_t outBase,
+                                                uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist)
+{
+    const int tid = threadIdx.x;
+    // scratch inside order[] (unused in this mode): two work lists and the evaluated bitmap
+    uint16_t *listA = sm.order, *listB = sm.order + 1024;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(sm.order + 2048);          // 128 words = 4096 bits
+    const size_t tileOut = outBase + (size_t)(regionBase + MT_HALO);
+    // literal placeholder everywhere; evaluated positions overwrite it after the barrier
+    reinterpret_cast<uint4 *>(lenCode + tileOut)[tid] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4 *>(dist + tileOut)[tid] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4 *>(dist + tileOut)[tid + MT_THREADS] = make_uint4(0, 0, 0, 0);
+    if (tid < 128) bits[tid] = 0;
+    constexpr int kEntries = kParseEntries;                                  // 258
+    constexpr int kFirstSpec = (kEntries + MT_SPEC_STRIDE - 1) / MT_SPEC_STRIDE;   // first speculative start beyond the entries
+    constexpr int kSpecs = MT_TILE / MT_SPEC_STRIDE - kFirstSpec;
+    for (int j = tid; j < kEntries + kSpecs; j += MT_THREADS)
+        listA[j] = (uint16_t)(j < kEntries ? j : (kFirstSpec + (j - kEntries)) * MT_SPEC_STRIDE);
+    if (tid == 0) { sm.binCount[0] = kEntries + kSpecs; sm.binCount[1] = 0; }
+    __syncthreads();
+    uint16_t *cur = listA, *nxt = listB;
+    for (;;) {
+        const uint32_t count = sm.binCount[0];
+        if (count == 0) break;
+        for (uint32_t j = tid; j < count; j += MT_THREADS) {
+            const int p = cur[j];
+            if (p >= tileSlots) continue;
+            const uint32_t bit = 1u << (p & 31);
+            if (atomicOr(&bits[p >> 5], bit) & bit) continue;                // someone else owns this position
+            const int si = MT_HALO + p;
+            const int i = regionBase + si;
+            const int cap = min(kMaxLen, n - 1 - i);
+            int bestL = 0, bestS = 0;
+            if (i > 0 && cap >= kMinLen) match_one(ctx, si, cap, bestL, bestS);
+            const bool hit = bestL >= kMinLen;
+            lenCode[outBase + i] = hit ? (uint8_t)(bestL - 2) : (uint8_t)0;
+            dist[outBase + i] = hit ? (uint16_t)(si - bestS) : (uint16_t)0;
+            const int nx = p + (hit ? bestL : 0) + 1;                        // next parse cursor if p is one
+            if (nx < tileSlots && !((bits[nx >> 5] >> (nx & 31)) & 1u)) nxt[atomicAdd(&sm.binCount[1], 1u)] = (uint16_t)nx;
+        }
+        __syncthreads();
+        if (tid == 0) { sm.binCount[0] = sm.binCount[1]; sm.binCount[1] = 0; }
+        uint16_t *t = cur; cur = nxt; nxt = t;
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(MT_THREADS)
 k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
-        uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist)
+        uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist, int forceEager)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     MatchSmem &sm = *reinterpret_cast<MatchSmem *>(smem_raw);
@@ -129,15 +307,17 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         }
         reinterpret_cast<uint4 *>(sm.xs)[v] = q;
     }
-    for (int k = tid; k < MT_NSUB * MT_HB; k += MT_THREADS) sm.head[k] = MT_NONE;
+    for (int k = tid; k < MT_NSUB * MT_HB / 2; k += MT_THREADS) reinterpret_cast<uint32_t *>(sm.head)[k] = 0xFFFFFFFFu;
+    for (int k = tid; k < MT_NSUB * MT_HB / 8; k += MT_THREADS) reinterpret_cast<uint32_t *>(sm.pop)[k] = 0u;
     if (tid < MT_BINS) sm.binCount[tid] = 0;
-    if (tid == 0) sm.maxPop = 0;
+    if (tid == 0) { sm.maxPop = 0; sm.probeSum = 0; }
     __syncthreads();
 
     // ---- ascending hash chains, one warp per sub-region ---------------------------------
     if (warp < MT_NSUB) {
         const int sr = warp;
-        uint32_t *head = sm.head + sr * MT_HB;
+        uint16_t *head = sm.head + sr * MT_HB;
+        uint8_t *pop = sm.pop + sr * (MT_HB / 2);
         uint32_t myMax = 0;
         for (int ch = MT_SUB / 32 - 1; ch >= 0; ch--) {
             const int slot = sr * MT_SUB + ch * 32 + lane;
@@ -147,15 +327,16 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const uint32_t key = valid ? h : (0x80000000u | lane);
             const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
             const uint32_t higher = (lane == 31) ? 0u : (grp & ~((2u << lane) - 1u));
-            uint32_t old = MT_NONE;
-            if (valid) old = head[h];
+            uint32_t old = MT_NONE, oldPop = 0;
+            if (valid) { old = head[h]; oldPop = pop[h >> 1]; }
             __syncwarp();
             if (valid) {
-                sm.up[slot] = higher ? (uint16_t)(sr * MT_SUB + ch * 32 + (__ffs(higher) - 1)) : (uint16_t)(old & 0xFFFF);
+                sm.up[slot] = higher ? (uint16_t)(sr * MT_SUB + ch * 32 + (__ffs(higher) - 1)) : (uint16_t)old;
                 if ((grp & ((1u << lane) - 1u)) == 0) {
-                    const uint32_t pop = (old >> 16) + __popc(grp);
-                    head[h] = (uint32_t)slot | (pop << 16);
-                    myMax = max(myMax, pop);
+                    const uint32_t np = min(255u, oldPop + (uint32_t)__popc(grp));
+                    head[h] = (uint16_t)slot;
+                    pop[h >> 1] = (uint8_t)np;          // racy against the pair bucket's leader in this step: estimate only
+                    myMax = max(myMax, np);
                 }
             }
             __syncwarp();
@@ -172,113 +353,34 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
     const int tileSlots = min(MT_TILE, slotEnd - MT_HALO); // positions of this tile that exist
     const bool sorted = sm.maxPop > MT_SORT_THRESHOLD;
 
-    // ---- balance: counting sort of the tile's positions by estimated chain length --------------
-    if (sorted) {
-        for (int k = 0; k < MT_PER_THREAD; k++) {
-            const int idx = k * MT_THREADS + tid;
-            const int si = MT_HALO + idx;
-            uint32_t bn = 0xFF;
-            if (idx < tileSlots) {
-                const uint32_t h = hash24(lds_u32_unaligned(xsA + si), MT_HBITS);
-                const int lo = max(si - kWindow, minSlot);
-                uint32_t est = 0;
-                for (int sr = lo >> 10; sr <= (si >> 10); sr++) est += lds_u32(headA + 4 * (sr * MT_HB + h)) >> 16;
-                bn = 0;                                    // half-octave bins of the estimate
-                if (est) {
-                    const int msb = 31 - __clz(est);
-                    const int half = msb > 0 ? (int)((est >> (msb - 1)) & 1u) : 0;
-                    bn = (uint32_t)min(MT_BINS - 1, 1 + 2 * msb + half);
-                }
-                sm.bin[idx] = (uint8_t)bn;
-            }
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
-            if (bn != 0xFF && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&sm.binCount[bn], (uint32_t)__popc(grp));
-        }
-        __syncthreads();
-        if (tid == 0) {                                    // heaviest bin first
-            uint32_t acc = 0;
-            for (int bn = MT_BINS - 1; bn >= 0; bn--) { sm.binStart[bn] = acc; acc += sm.binCount[bn]; }
-        }
-        __syncthreads();
-        for (int k = 0; k < MT_PER_THREAD; k++) {
-            const int idx = k * MT_THREADS + tid;
-            const uint32_t bn = idx < tileSlots ? (uint32_t)sm.bin[idx] : 0xFFu;
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
-            const int leader = __ffs(grp) - 1;
-            uint32_t base = 0;
-            if (bn != 0xFF && lane == leader) base = atomicAdd(&sm.binStart[bn], (uint32_t)__popc(grp));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (bn != 0xFF) sm.order[base + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)(MT_HALO + idx);
-        }
-        __syncthreads();
-    }
-
-    // ---- per-position walk ----------------------------------------------------------------
-    // One flat loop over the chains of all overlapping sub-regions.  A visit loads the
-    // candidate's first eight bytes and tests them against a register copy of the position's
-    // own eight bytes under a mask covering bytes 0..bestL: a candidate that fails cannot beat
-    // the current best and costs ~20 straight-line instructions; only a candidate that passes
-    // (a strict improvement, a handful per position) gets its exact length computed, and only
-    // matches of eight bytes or more enter the extension loop.  Lanes therefore stay in lockstep
-    // for almost every visit.
-    const size_t outBase = (size_t)b * kBlockBytes;
     uint32_t xsB = xsA, headB = headA, upB = upA;            // opaque copies: keep the bases in registers
     asm volatile("" : "+r"(xsB), "+r"(headB), "+r"(upB));
-    const uint32_t orderA = smem_addr(sm.order);
-    for (int k = 0; k < MT_PER_THREAD; k++) {
-        const int idx = k * MT_THREADS + tid;
-        if (idx >= tileSlots) break;
-        const int si = sorted ? (int)lds_u16(orderA + 2 * idx) : MT_HALO + idx;
-        const int i = regionBase + si;
-        const int cap = min(kMaxLen, n - 1 - i);
-        int bestL = kMinLen - 1, bestS = 0;
-        if (i > 0 && cap >= kMinLen) {
-            const uint32_t xi = xsB + si;
-            const uint32_t wsi0 = lds_u32_unaligned(xi), wsi1 = lds_u32_unaligned(xi + 4);
-            const uint32_t h = hash24(wsi0, MT_HBITS);
-            const int lo = max(si - kWindow, minSlot);
-            const int srLast = si >> 10;
-            const int sr0 = lo >> 10;
-            // heads of the (at most three) chains to walk, loaded up front; -1 = no further chain
-            const uint32_t hp = headB + 4 * (sr0 * MT_HB + h);
-            int s = (int)(lds_u32(hp) & 0xFFFF);
-            int next1 = sr0 + 1 <= srLast ? (int)(lds_u32(hp + 4 * MT_HB) & 0xFFFF) : -1;
-            int next2 = sr0 + 2 <= srLast ? (int)(lds_u32(hp + 8 * MT_HB) & 0xFFFF) : -1;
-            while (s < lo) s = (int)lds_u16(upB + 2 * s);           // entries before the window (MT_NONE = 0xFFFF ends it)
-            uint32_t mLo = 0x00FFFFFFu, mHi = 0u;                   // bytes 0..bestL must agree to beat bestL
-            for (;;) {
-                if (s >= si) {                                      // chain exhausted (MT_NONE >= si as well)
-                    if (next1 < 0) break;
-                    s = next1; next1 = next2; next2 = -1;
-                    continue;
-                }
-                const int cur = s;
-                s = (int)lds_u16(upB + 2 * cur);
-                const uint32_t a = xsB + cur, al = a & ~3u, sh = (a & 3u) * 8;
-                const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4), w2 = lds_u32(al + 8);
-                const uint32_t d0 = __funnelshift_r(w0, w1, sh) ^ wsi0;
-                const uint32_t d1 = __funnelshift_r(w1, w2, sh) ^ wsi1;
-                if ((d0 & mLo) | (d1 & mHi)) continue;              // cannot beat the current best
-                // strict improvement (or, once bestL >= 8, a candidate agreeing on all eight bytes)
-                const unsigned long long d = ((unsigned long long)d1 << 32) | d0;
-                int m = d ? ((__ffsll((long long)d) - 1) >> 3) : 8;
-                if (m == 8 && cap > 8) {
-                    if (bestL > 8 && lds_u8(a + bestL) != lds_u8(xi + bestL)) continue;
-                    m = 8 + lcp_capped(xsB, cur + 8, si + 8, cap - 8);
-                }
-                m = min(m, cap);
-                if (m > bestL) {
-                    bestL = m; bestS = cur;
-                    if (m == cap) break;                            // nothing nearer can beat the cap
-                    const unsigned long long mk = c_byteMask[min(m, 8)];   // now bytes 0..m must agree
-                    mLo = (uint32_t)mk; mHi = (uint32_t)(mk >> 32);
-                }
+    MatchCtx ctx;
+    ctx.xsB = xsB; ctx.headB = headB; ctx.upB = upB; ctx.popB = smem_addr(sm.pop); ctx.minSlot = minSlot;
+
+    // ---- probe: sample 64 positions; a tile whose matches are long is evaluated lazily ---------
+    if (tid < MT_PROBES) {
+        const int si = MT_HALO + tid * (MT_TILE / MT_PROBES) + 1;
+        int L = 0;
+        if (si < slotEnd) {
+            const int i = regionBase + si;
+            const int cap = min(kMaxLen, n - 1 - i);
+            if (i > 0 && cap >= kMinLen) {
+                int bl = 0, bs = 0;
+                match_one(ctx, si, cap, bl, bs);
+                L = bl >= kMinLen ? bl : 0;
             }
         }
-        const bool hit = bestL >= kMinLen;
-        lenCode[outBase + i] = hit ? (uint8_t)(bestL - 2) : (uint8_t)0;
-        dist[outBase + i] = hit ? (uint16_t)(si - bestS) : (uint16_t)0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) L += __shfl_xor_sync(0xFFFFFFFFu, L, d);
+        if (lane == 0) atomicAdd(&sm.probeSum, (uint32_t)L);
     }
+    __syncthreads();
+    const size_t outBase = (size_t)b * kBlockBytes;
+    if (!forceEager && sm.probeSum >= MT_PROBES * MT_LONG_MEAN)
+        match_tile_lazy(sm, ctx, tileSlots, regionBase, n, outBase, lenCode, dist);
+    else
+        match_tile_eager(sm, ctx, sorted, tileSlots, regionBase, n, outBase, lenCode, dist);
 }
 
 int match_tiles_per_block() { return (kBlockBytes + MT_TILE - 1) / MT_TILE; }
@@ -290,11 +392,12 @@ void match_init()
     cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem));
 }
 
+// forceEager: evaluate every position (stage probe for tests); the product path passes false
 void launch_match(const uint8_t *in, const uint32_t *blkLen, uint8_t *lenCode, uint16_t *dist,
-                  uint32_t nBlocks, uint32_t maxLen, cudaStream_t st)
+                  uint32_t nBlocks, uint32_t maxLen, bool forceEager, cudaStream_t st)
 {
     dim3 grid((maxLen + MT_TILE - 1) / MT_TILE, nBlocks);
-    k_match<<<grid, MT_THREADS, sizeof(MatchSmem), st>>>(in, blkLen, lenCode, dist);
+    k_match<<<grid, MT_THREADS, sizeof(MatchSmem), st>>>(in, blkLen, lenCode, dist, forceEager ? 1 : 0);
 }
 
 } // namespace fcx

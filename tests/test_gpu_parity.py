@@ -59,6 +59,31 @@ def test_match_every_position(dc):
             name, bad[0], pg[bad[0]], lg[bad[0]], po[bad[0]], lo[bad[0]])
 
 
+def test_match_auto_mode_is_exact_wherever_a_parse_can_go(dc):
+    """Product-path run of the match kernel: tiles of long matches are evaluated lazily, so a
+    position may read 0 -- but never on the parse chain, and an evaluated position is exact."""
+    o = oracle()
+    bufs = [("phrases300k", datagen.phrases_block(300000, 3, 0)), ("zeros50k", np.zeros(50000, np.uint8)),
+            ("byterun9000", datagen.byte_run_block(9000, 6, 0)), ("periodic70k", datagen.periodic_block(70000, 4, 2)),
+            ("zipf64k", datagen.zipf_block(65536, 1, 0)),
+            ("mix", np.concatenate([datagen.phrases_block(20000, 5, 0), datagen.uniform_block(9000, 5, 1),
+                                    datagen.phrases_block(30000, 5, 2), datagen.zipf_block(9000, 5, 3)]))]
+    lazy_seen = False
+    for name, buf in bufs:
+        po, lo = o.match_all(buf)
+        lg, pg = dc.probe_match(_dev(buf), auto=True)
+        ev = lg != 0
+        assert np.array_equal(lg[ev], lo[ev]) and np.array_equal(pg[ev], po[ev]), name
+        i, chain = 0, []
+        while i < len(buf):
+            chain.append(i)
+            i += int(lo[i]) + 1
+        chain = np.array(chain)
+        assert np.array_equal(lg[chain], lo[chain]) and np.array_equal(pg[chain], po[chain]), name
+        lazy_seen |= bool(np.any((lg == 0) & (lo != 0)))
+    assert lazy_seen, "no tile took the lazy path: the test inputs no longer exercise it"
+
+
 def _oracle_streams(buf):
     o = oracle()
     p, l, c = o.lz77_parse(buf)
