@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libfcx.so")
+_LIB_PATH = os.environ.get("FCX_LIBFCX", os.path.join(_HERE, "libfcx.so"))   # override: tuning sweeps only
 _lib = None
 
 BLOCK_BYTES = 1 << 20

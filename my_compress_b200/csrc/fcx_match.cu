@@ -25,7 +25,7 @@
 // Long-match tiles are handled lazily.  A 64-position probe measures the mean match length;
 // when it is large, almost every position lies inside a match of an earlier position and will
 // never be a parse cursor.  The parse can only enter a tile at offsets 0..257, so such a tile
-// evaluates exactly those 258 positions plus a speculative chain start every 64 positions, and
+// evaluates exactly those 258 positions plus a speculative chain start every 32 positions, and
 // follows next(p) = p + len + 1 from each until it lands on a position that is already
 // evaluated (chains merge after a token or two).  The evaluated set then contains every
 // possible entry and is closed under next(), so whatever the true entry turns out to be, the
@@ -39,14 +39,20 @@ constexpr int MT_SUB = 1024;
 constexpr int MT_HALO = 2048;
 constexpr int MT_REGION = MT_TILE + MT_HALO;     // 6144 slots
 constexpr int MT_NSUB = MT_REGION / MT_SUB;      // 6
-constexpr int MT_HBITS = 10;
+#ifndef FCX_MT_HBITS
+#define FCX_MT_HBITS 10          // 11 drops a resident CTA, 9 doubles collisions: both measured slower
+#endif
+#ifndef FCX_MT_SPEC_STRIDE
+#define FCX_MT_SPEC_STRIDE 32    // 16/32/64/128 measured on the phrase corpus: 32 best
+#endif
+constexpr int MT_HBITS = FCX_MT_HBITS;
 constexpr int MT_HB = 1 << MT_HBITS;             // buckets per sub-region
 constexpr int MT_LOOK = 272;                     // >= 257 + 8
 constexpr int MT_THREADS = 256;
 constexpr int MT_PER_THREAD = MT_TILE / MT_THREADS;   // 16
 constexpr int MT_PROBES = 64;                         // positions sampled per tile
 constexpr int MT_LONG_MEAN = 12;                      // mean probed match length that switches a tile to lazy evaluation
-constexpr int MT_SPEC_STRIDE = 64;                    // lazy mode: a speculative chain starts every 64 positions
+constexpr int MT_SPEC_STRIDE = FCX_MT_SPEC_STRIDE;                    // lazy mode: a speculative chain starts every 32 positions
 constexpr uint32_t MT_NONE = 0xFFFF;
 constexpr int MT_BINS = 32;
 constexpr uint32_t MT_SORT_THRESHOLD = 12;       // sort only when some bucket holds more than this
@@ -226,7 +232,7 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
 }
 
 // lazy mode (long-match tiles): evaluate the 258 possible parse entries and a speculative start
-// every 64 positions, then follow every chain until it lands on an evaluated position
+// every 32 positions, then follow every chain until it lands on an evaluated position
 __device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &ctx, int tileSlots,
                                                 int regionBase, int n, size_t outBase,
                                                 uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist)
