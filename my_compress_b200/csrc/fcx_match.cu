@@ -152,8 +152,8 @@ __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, in
         const uint32_t d1 = __funnelshift_r(w1, w2, sh) ^ wsi1;
         if ((d0 & mLo) | (d1 & mHi)) continue;          // cannot beat the current best
         // strict improvement (or, once bestL >= 7, a candidate agreeing on all eight bytes)
-        const unsigned long long d = ((unsigned long long)d1 << 32) | d0;
-        int m = d ? ((__ffsll((long long)d) - 1) >> 3) : 8;
+        const uint32_t dx = d0 ? d0 : d1;               // word holding the first differing byte
+        int m = dx ? (d0 ? 0 : 4) + ((__ffs(dx) - 1) >> 3) : 8;
         if (m == 8 && cap > 8) {
             if (bestL > 8 && lds_u8(a + bestL) != lds_u8(xi + bestL)) continue;
             m = 8 + lcp_capped(xsB, cur + 8, si + 8, cap - 8);
@@ -191,9 +191,14 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
             const int half = msb > 0 ? (int)((est >> (msb - 1)) & 1u) : 0;
             return (uint32_t)min(MT_BINS - 1, 1 + 2 * msb + half);
         };
+        // a thread bins the same 16 positions in both passes: keep the bins in registers (8 bits each)
+        uint32_t binPack[MT_PER_THREAD / 4];
+#pragma unroll
         for (int k = 0; k < MT_PER_THREAD; k++) {
             const int idx = k * MT_THREADS + tid;
             const uint32_t bn = idx < tileSlots ? pos_bin(idx) : 0xFFu;
+            if ((k & 3) == 0) binPack[k >> 2] = 0;
+            binPack[k >> 2] |= bn << (8 * (k & 3));
             const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
             if (bn != 0xFF && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&sm.binCount[bn], (uint32_t)__popc(grp));
         }
@@ -203,9 +208,10 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
             for (int bn = MT_BINS - 1; bn >= 0; bn--) { sm.binStart[bn] = acc; acc += sm.binCount[bn]; }
         }
         __syncthreads();
+#pragma unroll
         for (int k = 0; k < MT_PER_THREAD; k++) {
             const int idx = k * MT_THREADS + tid;
-            const uint32_t bn = idx < tileSlots ? pos_bin(idx) : 0xFFu;   // recomputed: cheaper than 4 KB of shared memory
+            const uint32_t bn = (binPack[k >> 2] >> (8 * (k & 3))) & 0xFFu;
             const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
             const int leader = __ffs(grp) - 1;
             uint32_t base = 0;
