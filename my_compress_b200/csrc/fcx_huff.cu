@@ -122,67 +122,51 @@ k_hist(Ws ws)
 }
 
 // =========================================================================================
-// tree + code table + serialised header, one warp per stream
+// tree + code table + serialised header, one 256-thread CTA per stream (thread = symbol)
 // =========================================================================================
-constexpr int TREE_WARPS = 4;
-
 struct TreeSmem {
     uint32_t key[256];
     uint32_t sw[256];      // sorted leaf weights
     uint32_t iw[256];      // internal node weights
-    uint32_t icode[256];   // code prefix of internal nodes
-    uint32_t tab[256];     // code | 1<<len per symbol
     uint16_t child[512];   // [2j],[2j+1]: tree index (leaf: symbol, internal: 512-R+j')
+    uint16_t parLeaf[256]; // leaf -> 2*parent + side
+    uint16_t parInt[256];  // internal node -> 2*parent + side (0xFFFF for the root)
     uint8_t ssym[256];     // sorted leaf symbols
-    uint8_t ilen[256];
     uint8_t hdr[kSegHdrStride];
+    unsigned long long bitsSum;
+    uint32_t maxlen;
 };
 
-__global__ void __launch_bounds__(TREE_WARPS * 32)
+__global__ void __launch_bounds__(256)
 k_tree(Ws ws, uint32_t nSeg)
 {
-    __shared__ TreeSmem smAll[TREE_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t s = blockIdx.x * TREE_WARPS + warp;
-    if (s >= nSeg) return;
-    TreeSmem &sm = smAll[warp];
+    __shared__ TreeSmem sm;
+    const int t = threadIdx.x;
+    const uint32_t s = blockIdx.x;
     uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
     const uint32_t S = si[SI_S];
-    if (S == 0 || si[SI_RAW]) return;                       // mc:989-990: empty stream emits nothing
+    if (S == 0 || si[SI_RAW]) return;                       // mc:989-990: empty stream emits nothing (CTA-uniform)
 
-    // ---- stable sort of the non-zero weights: unique key = weight<<8 | symbol ------------
-    uint32_t w[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int sym = lane + 32 * i;
-        w[i] = ws.segHist[(size_t)s * 256 + sym];
-        sm.key[sym] = w[i] ? ((w[i] << 8) | (uint32_t)sym) : 0xFFFFFFFFu;
-        sm.tab[sym] = 0;
+    // ---- stable sort of the non-zero weights: unique key = weight<<8 | symbol, rank by counting ----
+    const uint32_t w = ws.segHist[(size_t)s * 256 + t];
+    const uint32_t mine = w ? ((w << 8) | (uint32_t)t) : 0xFFFFFFFFu;
+    sm.key[t] = mine;
+    if (t == 0) { sm.bitsSum = 0; sm.maxlen = 0; }
+    __syncthreads();
+    if (w) {
+        uint32_t rank = 0;
+#pragma unroll 8
+        for (int m = 0; m < 256; m++) rank += (sm.key[m] < mine) ? 1u : 0u;
+        sm.ssym[rank] = (uint8_t)t;
+        sm.sw[rank] = w;
     }
-    __syncwarp();
-    uint32_t nz = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        if (w[i]) {
-            const uint32_t mine = sm.key[lane + 32 * i];
-            uint32_t rank = 0;
-            for (int m = 0; m < 256; m++) rank += (sm.key[m] < mine) ? 1u : 0u;
-            sm.ssym[rank] = (uint8_t)(lane + 32 * i);
-            sm.sw[rank] = w[i];
-            nz++;
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, d);
-    const uint32_t R = nz;
+    const uint32_t R = (uint32_t)__syncthreads_count(w != 0);
     const uint32_t Tn = R > 1 ? R - 1 : 0;                   // mc:1013-1019
     const uint32_t mapB = (2 * Tn + 7) / 8;                  // mc:1024-1026
-    __syncwarp();
+    const uint32_t base = 512 - R;                           // mc:569: first internal node index
 
-    uint32_t maxlen = 0;
-    if (lane == 0 && R >= 2) {
+    if (t == 0 && R >= 2) {
         // ---- two-queue merge (mc:575-607): on equal weight a leaf, then the older internal node, goes first
-        const uint32_t base = 512 - R;                       // mc:569
         uint32_t qa = 0, qb = 0, made = 0;
         while ((R - qa) + (made - qb) > 1) {
             uint32_t sum = 0;
@@ -192,61 +176,67 @@ k_tree(Ws ws, uint32_t nSeg)
                 if (qa >= R) leaf = false;
                 else if (qb >= made) leaf = true;
                 else leaf = sm.sw[qa] <= sm.iw[qb];
-                if (leaf) { sm.child[2 * made + side] = sm.ssym[qa]; sum += sm.sw[qa]; qa++; }
-                else { sm.child[2 * made + side] = (uint16_t)(base + qb); sum += sm.iw[qb]; qb++; }
+                if (leaf) {
+                    const uint32_t sym = sm.ssym[qa];
+                    sm.child[2 * made + side] = (uint16_t)sym;
+                    sm.parLeaf[sym] = (uint16_t)(2 * made + side);
+                    sum += sm.sw[qa]; qa++;
+                } else {
+                    sm.child[2 * made + side] = (uint16_t)(base + qb);
+                    sm.parInt[qb] = (uint16_t)(2 * made + side);
+                    sum += sm.iw[qb]; qb++;
+                }
             }
             sm.iw[made] = sum;
             made++;
         }
-        // ---- codes: bit k = k-th branch from the root, 0 = left (mc:869-917) ------------------
-        sm.icode[Tn - 1] = 0; sm.ilen[Tn - 1] = 0;
-        for (int j = (int)Tn - 1; j >= 0; j--) {
-            const uint32_t pc = sm.icode[j], pl = sm.ilen[j];
-#pragma unroll
-            for (uint32_t side = 0; side < 2; side++) {
-                const uint32_t ci = sm.child[2 * j + side];
-                const uint32_t cc = pl < 32 ? (pc | (side << pl)) : pc;
-                const uint32_t cl = pl + 1;
-                if (ci < 256) {
-                    sm.tab[ci] = cl <= 31 ? (cc | (1u << cl)) : 0u;
-                    if (cl > maxlen) maxlen = cl;
-                } else {
-                    sm.icode[ci - base] = cc; sm.ilen[ci - base] = (uint8_t)cl;
-                }
-            }
-        }
+        sm.parInt[Tn - 1] = 0xFFFF;                          // root
     }
-    maxlen = __shfl_sync(0xFFFFFFFFu, maxlen, 0);
+    __syncthreads();
+
+    // ---- codes: every leaf climbs to the root; bit k of the code = k-th branch from the root, 0 = left
+    uint32_t entry = 0, len = 0;
+    if (w && R >= 2) {
+        // climbing pushes the deepest branch first, so after the last shift the root's branch sits
+        // in bit 0 and the deepest in bit len-1: exactly "bit k = k-th branch from the root"
+        uint32_t code = 0;
+        uint32_t p = sm.parLeaf[t];
+        while (p != 0xFFFF && len < 33) {
+            code = (code << 1) | (p & 1u);
+            len++;
+            p = sm.parInt[p >> 1];
+        }
+        entry = (len >= 1 && len <= 31) ? (code | (1u << len)) : 0u;
+    }
+    ws.segTab[(size_t)s * 256 + t] = entry;
+    if (w) {
+        atomicMax(&sm.maxlen, len);
+        atomicAdd(&sm.bitsSum, (unsigned long long)w * len);
+    }
     // ---- serialised header: Tn | child-is-internal bitmap | (left,right) byte pairs ------------
-    for (uint32_t i = lane; i < 1 + mapB; i += 32) sm.hdr[i] = (i == 0) ? (uint8_t)Tn : (uint8_t)0;
-    __syncwarp();
-    if (lane == 0)
-        for (uint32_t j = 0; j < 2 * Tn; j++)
-            if (sm.child[j] >= 256) sm.hdr[1 + (j >> 3)] |= (uint8_t)(1u << (j & 7));   // mc:1035-1050
-    for (uint32_t j = lane; j < 2 * Tn; j += 32) {
+    if ((uint32_t)t < 1 + mapB) {
+        uint32_t v = 0;
+        if (t == 0) v = Tn;
+        else
+            for (int k = 0; k < 8; k++) {
+                const uint32_t j = 8 * (t - 1) + k;
+                if (j < 2 * Tn && sm.child[j] >= 256) v |= 1u << k;          // mc:1035-1050
+            }
+        sm.hdr[t] = (uint8_t)v;
+    }
+    for (uint32_t j = t; j < 2 * Tn; j += 256) {
         const uint32_t ci = sm.child[j];
         sm.hdr[1 + mapB + j] = (uint8_t)(ci >= 256 ? ci - 256 : ci);
     }
-    __syncwarp();
+    __syncthreads();
     const uint32_t hdrBytes = 1 + mapB + 2 * Tn;
-    for (uint32_t i = lane; i < hdrBytes; i += 32) ws.segHdr[(size_t)s * kSegHdrStride + i] = sm.hdr[i];
-    // ---- table out + total bits -----------------------------------------------------------------
-    unsigned long long bits = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int sym = lane + 32 * i;
-        const uint32_t e = sm.tab[sym];
-        ws.segTab[(size_t)s * 256 + sym] = e;
-        if (e) bits += (unsigned long long)w[i] * (uint32_t)(31 - __clz(e));
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
-    if (lane == 0) {
+    for (uint32_t i = t; i < hdrBytes; i += 256) ws.segHdr[(size_t)s * kSegHdrStride + i] = sm.hdr[i];
+    if (t == 0) {
         si[SI_R] = R;
         si[SI_HDR] = hdrBytes;
-        si[SI_W] = (uint32_t)((bits + 31) >> 5);             // mc:895-923: ceil(totalBits/32) words
-        si[SI_MAXLEN] = maxlen;
-        if (maxlen > 31) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_CODELEN);
+        si[SI_W] = (uint32_t)((sm.bitsSum + 31) >> 5);      // mc:895-923: ceil(totalBits/32) words
+        si[SI_MAXLEN] = sm.maxlen;
+        if (sm.maxlen > 31) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_CODELEN);
     }
 }
 
@@ -665,7 +655,7 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     if (mark) mark(markArg, 2);
     k_hist<<<numSM * 8, 256, 0, st>>>(ws); launches++;
     if (mark) mark(markArg, 3);
-    k_tree<<<(nSeg + TREE_WARPS - 1) / TREE_WARPS, TREE_WARPS * 32, 0, st>>>(ws, nSeg); launches++;
+    k_tree<<<nSeg, 256, 0, st>>>(ws, nSeg); launches++;
     if (mark) mark(markArg, 4);
     k_chunk_bits<<<numSM * 4, 256, 0, st>>>(ws); launches++;
     k_seg_scan<<<(nSeg + 255) / 256, 256, 0, st>>>(ws, nSeg); launches++;
