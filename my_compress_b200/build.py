@@ -22,6 +22,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+CLI = os.path.join(HERE, "fcx_cli")
+
+
+def build_cli(force=False):
+    """The flag-compatible CLI (my_compress_b200/cli/fcx_cli.cpp) linked against libfcx.so."""
+    src = os.path.join(HERE, "cli", "fcx_cli.cpp")
+    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return CLI
+    cmd = ["g++", "-O2", "-std=c++17", src, "-o", CLI, "-L" + HERE, "-lfcx", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building fcx_cli")
+    return CLI
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
@@ -36,4 +52,5 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
+    build_cli(force=True)
     print(LIB)

@@ -210,3 +210,28 @@ def test_multi_gpu_block_sharding_matches_single_gpu():
     for g in sorted({2, min(ndev, 4), ndev}):
         assert api.compress(data, n_gpus=g) == one, "differs with %d GPUs" % g
     assert one == _oracle_container(data)
+
+
+def test_cli_is_interchangeable_with_the_reference_cli(tmp_path):
+    """./fcx_cli takes the reference's flags (mc:3992-4053) and writes the same files: compare with the
+    reference CLI built by oracle/build_ref.sh, and cross-decompress in both directions."""
+    import subprocess
+
+    from _libs import REF_CLI
+    from my_compress_b200 import build
+
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/my_compress_ref not built")
+    cli = build.build_cli()
+    data = datagen.gen("mixed", (2 << 20) + 999, seed=4)
+    src = tmp_path / "in.bin"
+    src.write_bytes(data.tobytes())
+    ours, ref = tmp_path / "ours.fcx7", tmp_path / "ref.fcx7"
+    subprocess.check_call([cli, "-i", str(src), "-o", str(ours), "-c", "lz77"])
+    subprocess.check_call([REF_CLI, "-i", str(src), "-o", str(ref), "-c", "lz77"], stdout=subprocess.DEVNULL)
+    assert ours.read_bytes() == ref.read_bytes()
+    back1, back2 = tmp_path / "back1.bin", tmp_path / "back2.bin"
+    subprocess.check_call([REF_CLI, "-i", str(ours), "-o", str(back1)], stdout=subprocess.DEVNULL)   # reference decodes ours
+    subprocess.check_call([cli, "-i", str(ref), "-o", str(back2)])                                     # we decode the reference's
+    assert back1.read_bytes() == data.tobytes() and back2.read_bytes() == data.tobytes()
+    assert subprocess.call([cli, "-i", str(src), "-o", str(ours), "-c", "lz78"], stderr=subprocess.DEVNULL) == 255
