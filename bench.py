@@ -50,6 +50,16 @@ def env_int(name, default):
         return default
 
 
+def encode_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_encode per launch, from the committed ncu
+    --set full capture of this workload (profiles/encode_traffic.json); None if there is none."""
+    path = os.path.join(ROOT, "profiles", "encode_traffic.json")
+    try:
+        return json.load(open(path)).get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -74,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -273,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = alg_bytes / (enc_ms * 1e-3) / 1e9 if enc_ms > 0 else 0.0
     stage_total = sum(stage.values())
     roofline = {"kernel": "k_encode", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": encode_traffic(args.workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": enc_ms,
                 "share_of_step": enc_ms / stage_total if stage_total else None}
     match_ms = stage.get("match", 0.0)
