@@ -78,6 +78,7 @@ struct fcx_ctx {
     int numSM = 148;
     cudaStream_t stream = 0;
     uint32_t maxBlocks = 0;
+    uint32_t batchBlocks = 0;          // blocks per device batch (<= maxBlocks); 0 = maxBlocks
     Ws ws{};
     std::vector<void *> allocs;
     uint64_t launches = 0;
@@ -233,8 +234,17 @@ extern "C" int fcx_ctx_stage_times(fcx_ctx *c, const char **names, float *ms, in
 // -----------------------------------------------------------------------------------------
 // device-resident compress
 // -----------------------------------------------------------------------------------------
+// Optional per-batch hooks of the host-buffer path: batch k starts only after waitBefore[k]
+// (its H2D copy), and when it is done the running output cursor is copied to hostCursor[k]
+// (pinned) and recordAfter[k] fires, so the host can start that batch's D2H while batch k+1 runs.
+struct BatchHooks {
+    cudaEvent_t *waitBefore = nullptr;
+    cudaEvent_t *recordAfter = nullptr;
+    uint64_t *hostCursor = nullptr;
+};
+
 static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out, uint64_t outCap, uint32_t flags,
-                       uint64_t hdrBytes, uint32_t hdrBlocks)
+                       uint64_t hdrBytes, uint32_t hdrBlocks, const BatchHooks *hooks = nullptr)
 {
     const Ws &w = c->ws;
     cudaStream_t st = c->stream;
@@ -259,8 +269,11 @@ static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_o
         }
         return FCX_OK;
     }
-    for (uint64_t first = 0; first < nBlocks; first += c->maxBlocks) {
-        const uint32_t nb = (uint32_t)std::min<uint64_t>(c->maxBlocks, nBlocks - first);
+    const uint32_t step = c->batchBlocks ? std::min(c->batchBlocks, c->maxBlocks) : c->maxBlocks;
+    uint32_t batch = 0;
+    for (uint64_t first = 0; first < nBlocks; first += step, batch++) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(step, nBlocks - first);
+        if (hooks && hooks->waitBefore) CK(cudaStreamWaitEvent(st, hooks->waitBefore[batch], 0));
         const uint8_t *bin = d_in + first * kBlockBytes;
         const uint64_t rem = n - first * kBlockBytes;
         const uint32_t maxLen = (uint32_t)std::min<uint64_t>(rem, kBlockBytes);
@@ -274,6 +287,10 @@ static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_o
         c->launches += launch_huff_stage(w, nb, d_out, outCap, withHeader, (uint32_t)hdrBytes, hdrBlocks, 0, c->numSM, st,
                                          mark_stage, c);
         CK(cudaGetLastError());
+        if (hooks && hooks->recordAfter) {
+            CK(cudaMemcpyAsync(&hooks->hostCursor[batch], w.counters + C_CURSOR, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(hooks->recordAfter[batch], st));
+        }
     }
     return FCX_OK;
 }
@@ -330,9 +347,13 @@ struct DevSlot {
     uint32_t ctxBlocks = 0;
     uint8_t *dIn = nullptr, *dOut = nullptr;
     uint64_t inCap = 0, outCap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // kernels
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    std::vector<cudaEvent_t> evIn, evOut;   // per sub-batch
+    uint64_t *hostCursor = nullptr;         // pinned, per sub-batch
 };
 DevSlot g_slots[64];
+constexpr uint32_t kMaxPipeBatches = 64;
 
 // grow-only per-device scratch for the host-buffer API
 int slot_prepare(DevSlot &s, int dev, uint64_t inBytes, uint64_t outBytes)
@@ -340,7 +361,17 @@ int slot_prepare(DevSlot &s, int dev, uint64_t inBytes, uint64_t outBytes)
     CK(cudaSetDevice(dev));
     const uint64_t blocks = std::max<uint64_t>(1, (inBytes + kBlockBytes - 1) / kBlockBytes);
     const uint32_t want = (uint32_t)std::min<uint64_t>(blocks, 1024);
-    if (!s.stream) CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (!s.stream) {
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s.h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking));
+        CK(cudaHostAlloc(reinterpret_cast<void **>(&s.hostCursor), kMaxPipeBatches * sizeof(uint64_t), cudaHostAllocDefault));
+        s.evIn.resize(kMaxPipeBatches); s.evOut.resize(kMaxPipeBatches);
+        for (uint32_t k = 0; k < kMaxPipeBatches; k++) {
+            CK(cudaEventCreateWithFlags(&s.evIn[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.evOut[k], cudaEventDisableTiming));
+        }
+    }
     if (!s.ctx || s.ctxBlocks < want) {
         if (s.ctx) fcx_ctx_destroy(s.ctx);
         s.ctx = nullptr;
@@ -383,6 +414,9 @@ extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, ui
     std::vector<uint64_t> bytes(G, 0);
     std::vector<int> rcs(G, FCX_OK);
     std::vector<std::string> errs(G);
+    // One shard = one device.  The shard is cut into sub-batches so that the H2D copy of batch k+1
+    // and (single-device calls) the D2H copy of batch k-1 overlap the kernels of batch k.
+    const bool streamOut = (G == 1);
     auto shard = [&](size_t g) {
         DevSlot &s = g_slots[devs[g]];
         std::lock_guard<std::mutex> lk(s.mu);
@@ -390,11 +424,57 @@ extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, ui
         const uint64_t len = std::min<uint64_t>(n, b0[g + 1] * (uint64_t)kBlockBytes) - std::min<uint64_t>(n, off);
         const uint64_t bound = fcx_compress_bound(len);
         int rc = slot_prepare(s, devs[g], len, bound);
-        if (rc == FCX_OK && len) rc = cudaMemcpyAsync(s.dIn, in + off, len, cudaMemcpyHostToDevice, s.stream) == cudaSuccess
-                                           ? FCX_OK : fail(FCX_ERR_CUDA, "H2D copy failed");
-        if (rc == FCX_OK)
-            rc = fcx_compress_lz77_device(s.ctx, s.dIn, len, s.dOut, bound, g == 0 ? FCX_WITH_HEADER : 0, n, (uint32_t)nBlocks);
-        if (rc == FCX_OK) rc = fcx_ctx_finish(s.ctx, &bytes[g]);
+        if (rc) { rcs[g] = rc; errs[g] = g_err; return; }
+        const uint64_t blocks = (len + kBlockBytes - 1) / kBlockBytes;
+        // sub-batch size: >= 16 blocks keeps the GPU busy, <= 8 batches keeps per-batch latency small
+        uint32_t sb = (uint32_t)std::max<uint64_t>(16, (blocks + 7) / 8);
+        sb = std::min<uint32_t>(sb, s.ctxBlocks);
+        const uint32_t nBatches = blocks ? (uint32_t)((blocks + sb - 1) / sb) : 0;
+        if (nBatches < 2 || nBatches > kMaxPipeBatches) {                    // small input: nothing to overlap
+            s.ctx->batchBlocks = 0;
+            if (len && cudaMemcpyAsync(s.dIn, in + off, len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+                rc = fail(FCX_ERR_CUDA, "H2D copy failed");
+            if (rc == FCX_OK)
+                rc = fcx_compress_lz77_device(s.ctx, s.dIn, len, s.dOut, bound, g == 0 ? FCX_WITH_HEADER : 0, n, (uint32_t)nBlocks);
+            if (rc == FCX_OK) rc = fcx_ctx_finish(s.ctx, &bytes[g]);
+            if (rc == FCX_OK && streamOut) {
+                if (bytes[g] > outCap) rc = fail(FCX_ERR_CAPACITY, "output buffer smaller than the compressed result");
+                else if (cudaMemcpyAsync(out, s.dOut, bytes[g], cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
+                         cudaStreamSynchronize(s.stream) != cudaSuccess) rc = fail(FCX_ERR_CUDA, "D2H copy failed");
+            }
+            rcs[g] = rc;
+            if (rc) errs[g] = g_err;
+            return;
+        }
+        cudaError_t e = cudaSuccess;
+        for (uint32_t k = 0; k < nBatches && e == cudaSuccess; k++) {
+            const uint64_t o = (uint64_t)k * sb * kBlockBytes, l = std::min<uint64_t>((uint64_t)sb * kBlockBytes, len - o);
+            e = cudaMemcpyAsync(s.dIn + o, in + off + o, l, cudaMemcpyHostToDevice, s.h2d);
+            if (e == cudaSuccess) e = cudaEventRecord(s.evIn[k], s.h2d);
+        }
+        if (e != cudaSuccess) { rcs[g] = fail(FCX_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); errs[g] = g_err; return; }
+        BatchHooks hooks;
+        hooks.waitBefore = s.evIn.data(); hooks.recordAfter = s.evOut.data(); hooks.hostCursor = s.hostCursor;
+        s.ctx->batchBlocks = sb;
+        if (((uintptr_t)s.dIn & 15) || ((uintptr_t)s.dOut & 15)) rc = fail(FCX_ERR_ARG, "device pointers must be 16-byte aligned");
+        if (rc == FCX_OK) rc = run_batches(s.ctx, s.dIn, len, s.dOut, bound, g == 0 ? FCX_WITH_HEADER : 0, n, (uint32_t)nBlocks, &hooks);
+        s.ctx->batchBlocks = 0;
+        if (rc == FCX_OK && streamOut) {
+            uint64_t prev = 0;
+            for (uint32_t k = 0; k < nBatches && rc == FCX_OK; k++) {
+                if (cudaEventSynchronize(s.evOut[k]) != cudaSuccess) { rc = fail(FCX_ERR_CUDA, "batch failed"); break; }
+                const uint64_t cur = s.hostCursor[k];
+                if (cur > outCap || cur > bound) { rc = fail(FCX_ERR_CAPACITY, "output buffer smaller than the compressed result"); break; }
+                if (cur > prev && cudaMemcpyAsync(out + prev, s.dOut + prev, cur - prev, cudaMemcpyDeviceToHost, s.d2h) != cudaSuccess)
+                    rc = fail(FCX_ERR_CUDA, "D2H copy failed");
+                prev = cur;
+            }
+        }
+        uint64_t got = 0;
+        const int frc = fcx_ctx_finish(s.ctx, &got);                         // syncs the kernel stream, reports device-side errors
+        if (rc == FCX_OK) rc = frc;
+        if (rc == FCX_OK && streamOut && cudaStreamSynchronize(s.d2h) != cudaSuccess) rc = fail(FCX_ERR_CUDA, "D2H copy failed");
+        bytes[g] = got;
         rcs[g] = rc;
         if (rc) errs[g] = g_err;
     };
@@ -408,6 +488,7 @@ extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, ui
     uint64_t total = 0;
     for (size_t g = 0; g < G; g++) total += bytes[g];
     if (total > outCap) return fail(FCX_ERR_CAPACITY, "output buffer smaller than the compressed result");
+    if (streamOut) { *outN = total; return FCX_OK; }                     // already copied batch by batch
     // place the shards: only their byte counts cross devices (host prefix sum)
     uint64_t at = 0;
     for (size_t g = 0; g < G; g++) {
