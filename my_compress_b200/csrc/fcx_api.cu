@@ -427,7 +427,13 @@ extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, ui
         if (rc) { rcs[g] = rc; errs[g] = g_err; return; }
         const uint64_t blocks = (len + kBlockBytes - 1) / kBlockBytes;
         // sub-batch size: >= 16 blocks keeps the GPU busy, <= 8 batches keeps per-batch latency small
-        uint32_t sb = (uint32_t)std::max<uint64_t>(16, (blocks + 7) / 8);
+#ifndef FCX_PIPE_MIN_BLOCKS
+#define FCX_PIPE_MIN_BLOCKS 16
+#endif
+#ifndef FCX_PIPE_MAX_BATCHES
+#define FCX_PIPE_MAX_BATCHES 8
+#endif
+        uint32_t sb = (uint32_t)std::max<uint64_t>(FCX_PIPE_MIN_BLOCKS, (blocks + FCX_PIPE_MAX_BATCHES - 1) / FCX_PIPE_MAX_BATCHES);
         sb = std::min<uint32_t>(sb, s.ctxBlocks);
         const uint32_t nBatches = blocks ? (uint32_t)((blocks + sb - 1) / sb) : 0;
         if (nBatches < 2 || nBatches > kMaxPipeBatches) {                    // small input: nothing to overlap

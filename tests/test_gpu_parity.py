@@ -170,6 +170,7 @@ def _oracle_container(data):
     ("uniform", (4 << 20) + 1),          # config 5 family, 1-byte last block
     ("byterun", (1 << 20) + 5000),       # worst case for the match finder
     ("periodic", 3 << 20),
+    ("mixed", (40 << 20) + 5),           # > 16 blocks: the host path runs as a pipeline of sub-batches
 ])
 def test_container_vs_oracle(family, nbytes):
     data = datagen.gen(family, nbytes, seed=11)
@@ -235,3 +236,23 @@ def test_cli_is_interchangeable_with_the_reference_cli(tmp_path):
     subprocess.check_call([cli, "-i", str(ref), "-o", str(back2)])                                     # we decode the reference's
     assert back1.read_bytes() == data.tobytes() and back2.read_bytes() == data.tobytes()
     assert subprocess.call([cli, "-i", str(src), "-o", str(ours), "-c", "lz78"], stderr=subprocess.DEVNULL) == 255
+
+
+def test_device_context_with_small_batches_and_capacity_error(dc):
+    """A context whose batch (8 blocks here, see the fixture) is smaller than the input walks the blocks
+    batch by batch with a device-side output cursor; an undersized output buffer is reported, not overrun."""
+    import torch
+
+    data = datagen.gen("mixed", (19 << 20) + 123, seed=8)            # 20 blocks -> 3 batches of <= 8
+    d_in = _dev(data)
+    want = _oracle_container(data)
+    d_out = torch.zeros(api.compress_bound(len(data)), dtype=torch.uint8, device="cuda")
+    _, n = dc.compress(d_in, d_out)
+    assert bytes(d_out[:n].cpu().numpy()) == want
+    small = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")    # far too small for 20 blocks
+    with pytest.raises(api.FcxError) as e:
+        dc.compress(d_in, small)
+    assert e.value.code == -4                                          # FCX_ERR_CAPACITY
+    assert bytes(small[-16:].cpu().numpy()) == bytes(16)               # nothing written past / near the end
+    _, n2 = dc.compress(d_in, d_out)                                   # the context is still usable
+    assert n2 == n
