@@ -149,6 +149,7 @@ extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks
     A(dalloc(c, &w.segBitBase, B * 4));
     A(dalloc(c, &w.chunkSeg, (size_t)w.maxChunks));
     A(dalloc(c, &w.chunkHist, (size_t)w.maxChunks * 256));
+    A(dalloc(c, &w.chunkSlow, (size_t)w.maxChunks));
     A(dalloc(c, &w.chunkBits, (size_t)w.maxChunks));
     A(dalloc(c, &w.chunkBitOff, (size_t)w.maxChunks));
     A(dalloc(c, &w.blkOff, B + 1));

@@ -41,7 +41,7 @@ enum { M_T = 0, M_PC, M_G, M_GBITS, M_S0, M_S1, M_S2, M_S3, M_WORDS };
 // per-segment info words
 enum { SI_S = 0, SI_R, SI_HDR, SI_W, SI_FIRST_CHUNK, SI_NCHUNKS, SI_RAW, SI_MAXLEN, SI_WORDS };
 // totals words
-enum { TOT_CHUNKS = 0, TOT_ERR, TOT_WORDS = 8 };
+enum { TOT_CHUNKS = 0, TOT_ERR, TOT_SLOW, TOT_WORDS = 8 };
 // 64-bit counters
 enum { C_CURSOR = 0, C_SIN, C_SOUT, C_TOKENS, C_MATCHES, C_BLOCKS, C_LAST_BYTES, C_WORDS = 8 };
 
@@ -67,6 +67,7 @@ struct Ws {
     uint64_t *segBitBase; // [4*maxBlocks] absolute bit position (in d_out) of code word 0
     uint32_t *chunkSeg;   // [maxChunks]
     uint16_t *chunkHist;  // [maxChunks][256]
+    uint8_t *chunkSlow;   // [maxChunks] 1 = codes > 16 bits or too dense for the stage: handled by k_encode_slow
     uint32_t *chunkBits;  // [maxChunks]
     uint32_t *chunkBitOff;// [maxChunks] bit offset inside the segment's code words
     uint64_t *blkOff;     // [maxBlocks+1] byte offset (in d_out) of each "u32 size|payload" record

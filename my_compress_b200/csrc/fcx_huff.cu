@@ -266,6 +266,12 @@ k_chunk_bits(Ws ws)
 }
 
 // chunk bit offsets inside each stream (<= 128 chunks per stream: one thread per stream)
+#ifndef FCX_ENC_STAGE_WORDS
+#define FCX_ENC_STAGE_WORDS 4060      // tests build a variant with a tiny stage to exercise the dense path
+#endif
+constexpr uint32_t kEncStageWords = FCX_ENC_STAGE_WORDS;
+constexpr uint32_t kEncStageBits = kEncStageWords * 32;
+
 __global__ void __launch_bounds__(256)
 k_seg_scan(Ws ws, uint32_t nSeg)
 {
@@ -273,11 +279,17 @@ k_seg_scan(Ws ws, uint32_t nSeg)
     if (s >= nSeg) return;
     const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
     const uint32_t first = si[SI_FIRST_CHUNK], nch = si[SI_NCHUNKS];
-    uint32_t off = 0;
+    uint32_t off = 0, slow = 0;
+    const bool longCodes = si[SI_MAXLEN] > 24;               // fast path keeps a code in 24 bits (GROUP 1) or merges 2 / 4 into 32
     for (uint32_t c = 0; c < nch; c++) {
+        const uint32_t bits = ws.chunkBits[first + c];
         ws.chunkBitOff[first + c] = off;
-        off += ws.chunkBits[first + c];
+        const bool sl = si[SI_W] != 0 && (longCodes || bits > kEncStageBits - 128);   // does not fit the stage at any alignment
+        ws.chunkSlow[first + c] = sl ? 1 : 0;
+        slow += sl ? 1u : 0u;
+        off += bits;
     }
+    if (slow) atomicAdd(&ws.totals[TOT_SLOW], slow);
     if (nch && ((off + 31) >> 5) != si[SI_W]) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_INTERNAL);
 }
 
@@ -375,7 +387,7 @@ k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
 constexpr int ENC_THREADS = 256;
 constexpr int ENC_RUN = kChunkSyms / ENC_THREADS;     // 32 symbols per thread
 static_assert(ENC_RUN == 32, "run length is baked into the carry logic (>= 32 bits per run)");
-constexpr int ENC_STAGE_WORDS = 4060;                 // 16 bits per symbol on average; denser chunks take the slow path
+constexpr int ENC_STAGE_WORDS = (int)kEncStageWords;                 // 16 bits per symbol on average; denser chunks take the slow path
 
 struct EncSmem {
     uint32_t tab[256 * 32];            // fast path: code | len<<24; generic path: code | 1<<len
@@ -438,12 +450,188 @@ __device__ __forceinline__ void enc_pack_generic(const uint32_t (&ent)[32], uint
     tail = (uint32_t)acc; tailIdx = (w - stageA) >> 2;
 }
 
-__global__ void __launch_bounds__(ENC_THREADS)
+// ---- fast kernel -------------------------------------------------------------------------
+// Table entries are {code, len} pairs read with one 64-bit shared load (no extraction ops),
+// replicated 16x: lanes l and l+16 share a copy but sit in different half-warp phases of a
+// 64-bit access, so the look-ups stay conflict-free at the same 32 KB as before.  Codes are
+// merged GROUP at a time while they are looked up (4 when no code exceeds 8 bits, 2 up to 16,
+// 1 up to 24), so the pack pass only inserts 8 or 16 words per run in the common cases.
+struct EncFastSmem {
+    alignas(16) unsigned long long tab[256 * 16];      // tab[sym*16 + (lane & 15)] = code | (u64)len << 32
+    alignas(16) uint32_t stage[ENC_STAGE_WORDS + 8];
+    uint32_t warpBits[8];
+    uint32_t warpTail[8];
+};
+
+__device__ __forceinline__ uint2 enc_lds64(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+template <int GROUP>
+__device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__restrict__ out32, const uint8_t *src,
+                                                   uint32_t cnt, unsigned long long gb0, uint32_t tabLane, uint32_t stageA)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nRuns = cnt / ENC_RUN;
+    const bool active = (uint32_t)tid < nRuns;
+    constexpr int NG = 32 / GROUP;
+    // GROUP 4 / 2: g = merged codes, gl = their total length.  GROUP 1 (codes up to 24 bits): one
+    // register per symbol, code | len << 24, and gl is not used.
+    uint32_t g[NG], gl[GROUP == 1 ? 1 : NG];
+    uint32_t myBits = 0;
+    if (active) {
+        const uint4 a = reinterpret_cast<const uint4 *>(src)[tid * 2];
+        const uint4 d = reinterpret_cast<const uint4 *>(src)[tid * 2 + 1];
+        const uint32_t sy[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int q = 0; q < NG; q++) {
+            uint32_t acc = 0, len = 0;
+#pragma unroll
+            for (int k = 0; k < GROUP; k++) {
+                const int j = q * GROUP + k;
+                const uint32_t sym = __byte_perm(sy[j >> 2], 0u, 0x4440u + (j & 3));
+                const uint2 e = enc_lds64(tabLane + (sym << 7));
+                acc |= e.x << len;
+                len += e.y;
+            }
+            if (GROUP == 1) g[q] = acc | (len << 24);
+            else { g[q] = acc; gl[q] = len; }
+            myBits += len;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NG; q++) g[q] = 0;
+    }
+    // ---- CTA scan of the run lengths --------------------------------------------------------
+    uint32_t inc = myBits;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) sm.warpBits[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, fullBits = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t v = sm.warpBits[w]; if (w < warp) wbase += v; fullBits += v; }
+    // stage word k holds container word wBase + k (wBase a multiple of 4: 16-byte units line up)
+    const uint32_t r0 = (uint32_t)(gb0 & 127);
+    const unsigned long long wBase = (gb0 >> 5) & ~3ull;
+    const uint32_t p0 = r0 + wbase + inc - myBits;
+    // ---- pack: insert the groups, flush the low word of the 64-bit accumulator -----------------
+    uint32_t tail = 0, tailIdx = 0;
+    if (active) {
+        uint32_t lo = 0, hi = 0, accBits = p0 & 31, w = stageA + 4 * (p0 >> 5);
+#pragma unroll
+        for (int q = 0; q < NG; q++) {
+            const uint32_t bitsq = GROUP == 1 ? (g[q] & 0xFFFFFFu) : g[q];
+            const uint32_t lenq = GROUP == 1 ? (g[q] >> 24) : gl[q];
+            lo |= bitsq << accBits;
+            hi |= __funnelshift_l(bitsq, 0u, accBits);     // bits that spill past bit 31 (0 when accBits == 0)
+            accBits += lenq;
+            if (accBits >= 32) { enc_sts(w, lo); w += 4; lo = hi; hi = 0; accBits -= 32; }
+        }
+        tail = lo; tailIdx = (w - stageA) >> 2;
+    }
+    // the tail of run t-1 lives in the low bits of the head word of run t
+    const uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+    if (lane == 31) sm.warpTail[warp] = tail;
+    if (active) {
+        if (lane > 0) sm.stage[p0 >> 5] |= prevTail;                 // own word, own earlier store
+        if ((uint32_t)tid == nRuns - 1) sm.stage[tailIdx] = tail;    // nobody follows: park the tail
+    }
+    __syncthreads();
+    if (active && lane == 0 && warp > 0) sm.stage[p0 >> 5] |= sm.warpTail[warp - 1];
+    __syncthreads();
+    // ---- copy out: whole 16-byte units as 128-bit stores, shared edge words by atomicOr --------
+    const uint32_t first = r0 >> 5, fbit = r0 & 31;
+    const uint32_t endBit = r0 + fullBits, last = endBit >> 5, rem = endBit & 31;
+    uint32_t *dst = out32 + wBase;
+    const uint32_t vBeg = (first + (fbit ? 1u : 0u) + 3u) >> 2, vEnd = last >> 2;
+    if (vBeg < vEnd) {
+        for (uint32_t v = vBeg + tid; v < vEnd; v += ENC_THREADS)
+            reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(sm.stage)[v];
+        if (tid < 8) {                                               // scalar edges
+            const uint32_t k = tid < 4 ? first + tid : 4 * vEnd + (tid - 4);
+            const bool inHead = tid < 4 && k < 4 * vBeg, inTail = tid >= 4 && k < last;
+            if (inHead || inTail) {
+                if (k == first && fbit) atomicOr(&dst[k], sm.stage[k]); else dst[k] = sm.stage[k];
+            }
+        }
+    } else {
+        for (uint32_t k = first + tid; k < last; k += ENC_THREADS) {
+            if (k == first && fbit) atomicOr(&dst[k], sm.stage[k]); else dst[k] = sm.stage[k];
+        }
+    }
+    if (tid == 0 && rem && nRuns) atomicOr(&dst[last], sm.stage[last]);
+    return fullBits;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 4)
 k_encode(Ws ws, uint32_t *__restrict__ out32)
+{
+    __shared__ EncFastSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (ws.totals[TOT_ERR]) return;                     // capacity / internal error: write nothing
+    const uint32_t nChunks = ws.totals[TOT_CHUNKS];
+    const uint32_t per = (nChunks + gridDim.x - 1) / gridDim.x;
+    const uint32_t cBeg = blockIdx.x * per, cEnd = min(nChunks, cBeg + per);
+    const uint32_t tabLane = enc_smem_addr(sm.tab) + 8 * (lane & 15), stageA = enc_smem_addr(sm.stage);
+    uint32_t curSeg = 0xFFFFFFFFu, group = 4;
+    for (uint32_t chunk = cBeg; chunk < cEnd; chunk++) {
+        if (ws.chunkSlow[chunk]) continue;              // k_encode_slow's
+        const uint32_t s = ws.chunkSeg[chunk];
+        const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
+        if (si[SI_W] == 0) continue;                    // single-symbol stream: zero bits (mc:859)
+        if (s != curSeg) {
+            group = si[SI_MAXLEN] <= 8 ? 4u : si[SI_MAXLEN] <= 16 ? 2u : 1u;
+            __syncthreads();
+            const uint32_t e = ws.segTab[(size_t)s * 256 + tid];         // ENC_THREADS == 256 symbols; code | 1<<len
+            const uint32_t len = e ? (uint32_t)(31 - __clz(e)) : 0u;
+            const unsigned long long ent = (unsigned long long)(e ? (e ^ (1u << len)) : 0u) | ((unsigned long long)len << 32);
+#pragma unroll 4
+            for (int c = 0; c < 16; c++) sm.tab[tid * 16 + ((c + lane) & 15)] = ent;
+            curSeg = s;
+            __syncthreads();
+        }
+        const uint32_t b = s >> 2, k = s & 3;
+        const uint32_t c = chunk - si[SI_FIRST_CHUNK];
+        const uint32_t S = si[SI_S];
+        const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
+        const uint8_t *src = ws.strm[k] + (size_t)b * ws.strmStride[k] + (size_t)c * kChunkSyms;
+        const unsigned long long gb0 = ws.segBitBase[s] + ws.chunkBitOff[chunk];
+        const uint32_t fullBits = group == 4   ? enc_fast_chunk<4>(sm, out32, src, cnt, gb0, tabLane, stageA)
+                                  : group == 2 ? enc_fast_chunk<2>(sm, out32, src, cnt, gb0, tabLane, stageA)
+                                               : enc_fast_chunk<1>(sm, out32, src, cnt, gb0, tabLane, stageA);
+        // ---- ragged end of the stream (< 32 symbols): serial append ---------------------------
+        const uint32_t nRuns = cnt / ENC_RUN;
+        if (tid == 0 && cnt > nRuns * ENC_RUN) {
+            unsigned long long bp = gb0 + fullBits;
+            for (uint32_t i = nRuns * ENC_RUN; i < cnt; i++) {
+                const unsigned long long e = sm.tab[(uint32_t)src[i] * 16];
+                const unsigned long long v = (e & 0xFFFFFFFFull) << (bp & 31);
+                if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
+                if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
+                bp += (uint32_t)(e >> 32);
+            }
+        }
+        // no barrier here: the scan barrier of the next chunk orders this copy-out before the next
+        // pack, and warpBits / warpTail are rewritten only after barriers every thread has passed
+    }
+}
+
+// Generic kernel for the rare chunks the fast kernel skips (codes longer than 16 bits, or a chunk
+// too dense for the stage): sentinel table entries, one 64-bit insert per symbol, and for dense
+// chunks straight atomicOr into the container.  Exits at once when there is no such chunk.
+__global__ void __launch_bounds__(ENC_THREADS)
+k_encode_slow(Ws ws, uint32_t *__restrict__ out32)
 {
     __shared__ EncSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (ws.totals[TOT_ERR]) return;                     // capacity / internal error: write nothing
+    if (ws.totals[TOT_ERR] || ws.totals[TOT_SLOW] == 0) return;
     const uint32_t nChunks = ws.totals[TOT_CHUNKS];
     const uint32_t per = (nChunks + gridDim.x - 1) / gridDim.x;
     const uint32_t cBeg = blockIdx.x * per, cEnd = min(nChunks, cBeg + per);
@@ -453,10 +641,9 @@ k_encode(Ws ws, uint32_t *__restrict__ out32)
     for (uint32_t chunk = cBeg; chunk < cEnd; chunk++) {
         const uint32_t s = ws.chunkSeg[chunk];
         const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
-        if (si[SI_W] == 0) continue;                    // single-symbol stream: zero bits (mc:859)
+        if (!ws.chunkSlow[chunk]) continue;             // the fast kernel's
         if (s != curSeg) {
-            const uint32_t maxlen = si[SI_MAXLEN];
-            mode = maxlen <= 8 ? 4u : maxlen <= 16 ? 2u : maxlen <= 24 ? 1u : 0u;
+            mode = 0;                                   // always the generic representation here
             __syncthreads();
             uint32_t e = ws.segTab[(size_t)s * 256 + tid];      // ENC_THREADS == 256 symbols
             if (mode && e) { const uint32_t len = (uint32_t)(31 - __clz(e)); e = (e ^ (1u << len)) | (len << 24); }
@@ -662,6 +849,7 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, withHeader, outCap); launches++;
     if (mark) mark(markArg, 5);
     k_encode<<<numSM * 4, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
+    k_encode_slow<<<numSM * 2, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
     if (mark) mark(markArg, 6);
     k_headers<<<(nBlocks + 3) / 4, 128, 0, st>>>(ws, out, nBlocks, withHeader, hdrTotalBytes, hdrBlocks, batchStartCursor);
     launches++;
