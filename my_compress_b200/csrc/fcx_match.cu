@@ -371,7 +371,9 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
     ctx.xsB = xsB; ctx.headB = headB; ctx.upB = upB; ctx.popB = smem_addr(sm.pop); ctx.minSlot = minSlot;
 
     // ---- probe: sample 64 positions; a tile whose matches are long is evaluated lazily ---------
-    if (tid < MT_PROBES) {
+    // (only tiles with long chains can be expensive enough to need it: a tile whose every bucket is
+    // short is cheap to evaluate eagerly whatever its match lengths are)
+    if (sorted && tid < MT_PROBES) {
         const int si = MT_HALO + tid * (MT_TILE / MT_PROBES) + 1;
         int L = 0;
         if (si < slotEnd) {
