@@ -70,8 +70,8 @@ extern "C" uint64_t fcx_compress_bound(uint64_t n)
 // -----------------------------------------------------------------------------------------
 // context
 // -----------------------------------------------------------------------------------------
-enum { ST_MATCH = 0, ST_PARSE, ST_PLAN, ST_HIST, ST_TREE, ST_LAYOUT, ST_ENCODE, ST_HEADERS, ST_COUNT };
-static const char *kStageNames[ST_COUNT] = {"match", "parse", "plan", "hist", "tree", "layout", "encode", "headers"};
+enum { ST_MATCH = 0, ST_PARSE, ST_PLAN, ST_HIST, ST_TREE, ST_LAYOUT, ST_ENCODE, ST_ENCODE_SLOW, ST_HEADERS, ST_COUNT };
+static const char *kStageNames[ST_COUNT] = {"match", "parse", "plan", "hist", "tree", "layout", "encode", "encode_slow", "headers"};
 
 struct fcx_ctx {
     int device = 0;
@@ -152,6 +152,7 @@ extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks
     A(dalloc(c, &w.chunkSlow, (size_t)w.maxChunks));
     A(dalloc(c, &w.chunkBits, (size_t)w.maxChunks));
     A(dalloc(c, &w.chunkBitOff, (size_t)w.maxChunks));
+    A(dalloc(c, &w.chunkDesc, (size_t)w.maxChunks));
     A(dalloc(c, &w.blkOff, B + 1));
     A(dalloc(c, &w.totals, (size_t)TOT_WORDS));
     A(dalloc(c, &w.counters, (size_t)C_WORDS));

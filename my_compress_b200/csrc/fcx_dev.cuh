@@ -70,6 +70,7 @@ struct Ws {
     uint8_t *chunkSlow;   // [maxChunks] 1 = codes > 16 bits or too dense for the stage: handled by k_encode_slow
     uint32_t *chunkBits;  // [maxChunks]
     uint32_t *chunkBitOff;// [maxChunks] bit offset inside the segment's code words
+    uint4 *chunkDesc;     // [maxChunks] everything k_encode needs for one chunk (see CD_* in fcx_huff.cu)
     uint64_t *blkOff;     // [maxBlocks+1] byte offset (in d_out) of each "u32 size|payload" record
     uint32_t *totals;     // [TOT_WORDS]
     uint64_t *counters;   // [C_WORDS]

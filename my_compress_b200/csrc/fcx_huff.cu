@@ -265,12 +265,21 @@ k_chunk_bits(Ws ws)
     }
 }
 
-// chunk bit offsets inside each stream (<= 128 chunks per stream: one thread per stream)
+// chunk bit offsets inside each stream (<= 128 chunks per stream: one thread per stream), and the
+// 16-byte descriptor k_encode reads per chunk (runs after k_block_layout: needs segBitBase)
 #ifndef FCX_ENC_STAGE_WORDS
-#define FCX_ENC_STAGE_WORDS 4060      // tests build a variant with a tiny stage to exercise the dense path
+#define FCX_ENC_STAGE_WORDS 3064      // tests build a variant with a tiny stage to exercise the dense path
 #endif
 constexpr uint32_t kEncStageWords = FCX_ENC_STAGE_WORDS;
 constexpr uint32_t kEncStageBits = kEncStageWords * 32;
+
+// chunk descriptor: x = byte offset of the chunk inside its stream arena, z:w = absolute bit
+// position of its first code word bit in the container, y = the fields below
+constexpr uint32_t CD_CNT_MASK = 0x3FFFu;     // symbols in the chunk (<= 8192)
+constexpr int CD_K_SHIFT = 14;                // stream kind 0..3
+constexpr int CD_GROUP_SHIFT = 16;            // symbols merged per 32-bit insert: 4 / 3 / 2 / 1
+constexpr int CD_SKIP_SHIFT = 19;             // not the fast kernel's: single-symbol stream (no bits) or a slow chunk
+constexpr int CD_SEG_SHIFT = 20;              // stream id b*4+k (< 4096)
 
 __global__ void __launch_bounds__(256)
 k_seg_scan(Ws ws, uint32_t nSeg)
@@ -278,19 +287,30 @@ k_seg_scan(Ws ws, uint32_t nSeg)
     const uint32_t s = blockIdx.x * 256 + threadIdx.x;
     if (s >= nSeg) return;
     const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
-    const uint32_t first = si[SI_FIRST_CHUNK], nch = si[SI_NCHUNKS];
+    const uint32_t first = si[SI_FIRST_CHUNK], nch = si[SI_NCHUNKS], S = si[SI_S], W = si[SI_W];
+    const uint32_t maxlen = si[SI_MAXLEN];
     uint32_t off = 0, slow = 0;
-    const bool longCodes = si[SI_MAXLEN] > 24;               // fast path keeps a code in 24 bits (GROUP 1) or merges 2 / 4 into 32
+    const bool longCodes = maxlen > 24;                      // fast path keeps a code in 24 bits (GROUP 1) or merges 2..4 into 32
+    const uint32_t group = maxlen <= 8 ? 4u : maxlen <= 10 ? 3u : maxlen <= 16 ? 2u : 1u;
+    const uint32_t b = s >> 2, k = s & 3;
+    const unsigned long long bitBase = ws.segBitBase[s];
+    const uint32_t arena = b * ws.strmStride[k];
     for (uint32_t c = 0; c < nch; c++) {
         const uint32_t bits = ws.chunkBits[first + c];
         ws.chunkBitOff[first + c] = off;
-        const bool sl = si[SI_W] != 0 && (longCodes || bits > kEncStageBits - 128);   // does not fit the stage at any alignment
+        const bool sl = W != 0 && (longCodes || bits > kEncStageBits - 128);   // does not fit the stage at any alignment
         ws.chunkSlow[first + c] = sl ? 1 : 0;
         slow += sl ? 1u : 0u;
+        const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
+        const unsigned long long gb0 = bitBase + off;
+        const uint32_t skip = (sl || W == 0) ? 1u : 0u;
+        ws.chunkDesc[first + c] = make_uint4(arena + c * kChunkSyms,
+                                             cnt | (k << CD_K_SHIFT) | (group << CD_GROUP_SHIFT) | (skip << CD_SKIP_SHIFT) | (s << CD_SEG_SHIFT),
+                                             (uint32_t)gb0, (uint32_t)(gb0 >> 32));
         off += bits;
     }
     if (slow) atomicAdd(&ws.totals[TOT_SLOW], slow);
-    if (nch && ((off + 31) >> 5) != si[SI_W]) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_INTERNAL);
+    if (nch && ((off + 31) >> 5) != W) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_INTERNAL);
 }
 
 // =========================================================================================
@@ -453,12 +473,27 @@ __device__ __forceinline__ void enc_pack_generic(const uint32_t (&ent)[32], uint
 // ---- fast kernel -------------------------------------------------------------------------
 // Table entries are {code, len} pairs read with one 64-bit shared load (no extraction ops),
 // replicated 16x: lanes l and l+16 share a copy but sit in different half-warp phases of a
-// 64-bit access, so the look-ups stay conflict-free at the same 32 KB as before.  Codes are
-// merged GROUP at a time while they are looked up (4 when no code exceeds 8 bits, 2 up to 16,
-// 1 up to 24), so the pack pass only inserts 8 or 16 words per run in the common cases.
+// 64-bit access, so the look-ups stay conflict-free in 32 KB.  Codes are merged GROUP at a time
+// while they are looked up (4 when no code exceeds 8 bits, 3 up to 10, 2 up to 16, 1 up to 24),
+// so the pack pass inserts 8 / 11 / 16 / 32 words per run.
+//
+// Nothing in the chunk loop waits on global memory: the CTA copies the 16-byte descriptors of its
+// next 64 chunks to shared memory in one go, and the symbols of the NEXT chunk arrive by one TMA
+// bulk copy (cp.async.bulk + mbarrier, issued by thread 0 right after the scan barrier, when every
+// thread has consumed the buffer) while the current chunk is packed and copied out.  Only a change
+// of stream reloads the code table.
+//
+// Stage addressing is swizzled at 16-byte granularity (unit u lives at u ^ ((u >> 3) & 7)): runs
+// of equal length (uniform data: 8 words per run) would otherwise put every lane of a store on
+// the same four banks.  Whole units stay intact, so the copy-out still moves 128 bits at a time.
+constexpr int ENC_DESC_BATCH = 64;
+static_assert((ENC_STAGE_WORDS + 8) % 32 == 0, "the stage swizzle permutes inside aligned 32-word groups");
 struct EncFastSmem {
+    alignas(1024) uint32_t stage[ENC_STAGE_WORDS + 8];
     alignas(16) unsigned long long tab[256 * 16];      // tab[sym*16 + (lane & 15)] = code | (u64)len << 32
-    alignas(16) uint32_t stage[ENC_STAGE_WORDS + 8];
+    alignas(16) uint8_t sym[kChunkSyms];               // the chunk's symbols as they lie in the stream
+    alignas(16) uint4 desc[ENC_DESC_BATCH];
+    alignas(8) unsigned long long mbar;                // completion barrier of the bulk copy into sym
     uint32_t warpBits[8];
     uint32_t warpTail[8];
 };
@@ -470,21 +505,47 @@ __device__ __forceinline__ uint2 enc_lds64(uint32_t a)
     return v;
 }
 
+// byte offset of stage word k / index of stage unit v after the swizzle
+__device__ __forceinline__ uint32_t enc_swz_byte(uint32_t byteOff) { return byteOff ^ ((byteOff >> 3) & 0x70u); }
+__device__ __forceinline__ uint32_t enc_swz_word(uint32_t k) { return k ^ (((k >> 5) & 7u) << 2); }
+__device__ __forceinline__ uint32_t enc_swz_unit(uint32_t v) { return v ^ ((v >> 3) & 7u); }
+
+// one bulk copy global -> sym, completion signalled on mbar (one elected thread calls this)
+__device__ __forceinline__ void enc_bulk_fetch(uint32_t symA, uint32_t mbarA, const uint8_t *src, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbarA), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(symA), "l"(src), "r"(bytes), "r"(mbarA) : "memory");
+}
+__device__ __forceinline__ void enc_bulk_wait(uint32_t mbarA, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ENC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra ENC_WAIT_%=;\n"
+        "}\n" :: "r"(mbarA), "r"(phase) : "memory");
+}
+
 template <int GROUP>
-__device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__restrict__ out32, const uint8_t *src,
-                                                   uint32_t cnt, unsigned long long gb0, uint32_t tabLane, uint32_t stageA)
+__device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__restrict__ out32, uint32_t cnt,
+                                                   unsigned long long gb0, uint32_t tabLane, uint32_t stageA, uint32_t symA,
+                                                   uint32_t mbarA, uint32_t phase, const uint8_t *nextSrc, uint32_t nextRuns)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nRuns = cnt / ENC_RUN;
     const bool active = (uint32_t)tid < nRuns;
-    constexpr int NG = 32 / GROUP;
-    // GROUP 4 / 2: g = merged codes, gl = their total length.  GROUP 1 (codes up to 24 bits): one
+    constexpr int NG = (32 + GROUP - 1) / GROUP;
+    // GROUP 4 / 3 / 2: g = merged codes, gl = their total length.  GROUP 1 (codes up to 24 bits): one
     // register per symbol, code | len << 24, and gl is not used.
     uint32_t g[NG], gl[GROUP == 1 ? 1 : NG];
     uint32_t myBits = 0;
+    if (nRuns) enc_bulk_wait(mbarA, phase);
     if (active) {
-        const uint4 a = reinterpret_cast<const uint4 *>(src)[tid * 2];
-        const uint4 d = reinterpret_cast<const uint4 *>(src)[tid * 2 + 1];
+        uint4 a, d;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(symA + tid * 32));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(symA + tid * 32 + 16));
         const uint32_t sy[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
 #pragma unroll
         for (int q = 0; q < NG; q++) {
@@ -492,10 +553,12 @@ __device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__
 #pragma unroll
             for (int k = 0; k < GROUP; k++) {
                 const int j = q * GROUP + k;
-                const uint32_t sym = __byte_perm(sy[j >> 2], 0u, 0x4440u + (j & 3));
-                const uint2 e = enc_lds64(tabLane + (sym << 7));
-                acc |= e.x << len;
-                len += e.y;
+                if (j < 32) {
+                    const uint32_t sym = __byte_perm(sy[j >> 2], 0u, 0x4440u + (j & 3));
+                    const uint2 e = enc_lds64(tabLane + (sym << 7));
+                    acc |= e.x << len;
+                    len += e.y;
+                }
             }
             if (GROUP == 1) g[q] = acc | (len << 24);
             else { g[q] = acc; gl[q] = len; }
@@ -514,6 +577,8 @@ __device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__
     }
     if (lane == 31) sm.warpBits[warp] = inc;
     __syncthreads();
+    // every thread has consumed its symbols (myBits depends on all of them): refill the buffer
+    if (tid == 0 && nextRuns) enc_bulk_fetch(symA, mbarA, nextSrc, nextRuns * ENC_RUN);
     uint32_t wbase = 0, fullBits = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) { const uint32_t v = sm.warpBits[w]; if (w < warp) wbase += v; fullBits += v; }
@@ -524,27 +589,29 @@ __device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__
     // ---- pack: insert the groups, flush the low word of the 64-bit accumulator -----------------
     uint32_t tail = 0, tailIdx = 0;
     if (active) {
-        uint32_t lo = 0, hi = 0, accBits = p0 & 31, w = stageA + 4 * (p0 >> 5);
+        uint32_t lo = 0, accBits = p0 & 31, w = 4 * (p0 >> 5);
 #pragma unroll
         for (int q = 0; q < NG; q++) {
             const uint32_t bitsq = GROUP == 1 ? (g[q] & 0xFFFFFFu) : g[q];
             const uint32_t lenq = GROUP == 1 ? (g[q] >> 24) : gl[q];
             lo |= bitsq << accBits;
-            hi |= __funnelshift_l(bitsq, 0u, accBits);     // bits that spill past bit 31 (0 when accBits == 0)
+            const uint32_t hi = __funnelshift_l(bitsq, 0u, accBits);     // bits that spill past bit 31 (0 when accBits == 0)
             accBits += lenq;
-            if (accBits >= 32) { enc_sts(w, lo); w += 4; lo = hi; hi = 0; accBits -= 32; }
+            if (accBits >= 32) { enc_sts(stageA + enc_swz_byte(w), lo); w += 4; lo = hi; }
+            accBits &= 31;
         }
-        tail = lo; tailIdx = (w - stageA) >> 2;
+        tail = lo; tailIdx = w >> 2;
     }
     // the tail of run t-1 lives in the low bits of the head word of run t
     const uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
     if (lane == 31) sm.warpTail[warp] = tail;
+    const uint32_t headIdx = enc_swz_word(p0 >> 5);
     if (active) {
-        if (lane > 0) sm.stage[p0 >> 5] |= prevTail;                 // own word, own earlier store
-        if ((uint32_t)tid == nRuns - 1) sm.stage[tailIdx] = tail;    // nobody follows: park the tail
+        if (lane > 0) sm.stage[headIdx] |= prevTail;                            // own word, own earlier store
+        if ((uint32_t)tid == nRuns - 1) sm.stage[enc_swz_word(tailIdx)] = tail; // nobody follows: park the tail
     }
     __syncthreads();
-    if (active && lane == 0 && warp > 0) sm.stage[p0 >> 5] |= sm.warpTail[warp - 1];
+    if (active && lane == 0 && warp > 0) sm.stage[headIdx] |= sm.warpTail[warp - 1];
     __syncthreads();
     // ---- copy out: whole 16-byte units as 128-bit stores, shared edge words by atomicOr --------
     const uint32_t first = r0 >> 5, fbit = r0 & 31;
@@ -553,73 +620,98 @@ __device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__
     const uint32_t vBeg = (first + (fbit ? 1u : 0u) + 3u) >> 2, vEnd = last >> 2;
     if (vBeg < vEnd) {
         for (uint32_t v = vBeg + tid; v < vEnd; v += ENC_THREADS)
-            reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(sm.stage)[v];
+            reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(sm.stage)[enc_swz_unit(v)];
         if (tid < 8) {                                               // scalar edges
             const uint32_t k = tid < 4 ? first + tid : 4 * vEnd + (tid - 4);
             const bool inHead = tid < 4 && k < 4 * vBeg, inTail = tid >= 4 && k < last;
             if (inHead || inTail) {
-                if (k == first && fbit) atomicOr(&dst[k], sm.stage[k]); else dst[k] = sm.stage[k];
+                const uint32_t v = sm.stage[enc_swz_word(k)];
+                if (k == first && fbit) atomicOr(&dst[k], v); else dst[k] = v;
             }
         }
     } else {
         for (uint32_t k = first + tid; k < last; k += ENC_THREADS) {
-            if (k == first && fbit) atomicOr(&dst[k], sm.stage[k]); else dst[k] = sm.stage[k];
+            const uint32_t v = sm.stage[enc_swz_word(k)];
+            if (k == first && fbit) atomicOr(&dst[k], v); else dst[k] = v;
         }
     }
-    if (tid == 0 && rem && nRuns) atomicOr(&dst[last], sm.stage[last]);
+    if (tid == 0 && rem && nRuns) atomicOr(&dst[last], sm.stage[enc_swz_word(last)]);
     return fullBits;
 }
 
 __global__ void __launch_bounds__(ENC_THREADS, 4)
 k_encode(Ws ws, uint32_t *__restrict__ out32)
 {
-    __shared__ EncFastSmem sm;
+    extern __shared__ __align__(1024) unsigned char enc_smem_raw[];
+    EncFastSmem &sm = *reinterpret_cast<EncFastSmem *>(enc_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     if (ws.totals[TOT_ERR]) return;                     // capacity / internal error: write nothing
     const uint32_t nChunks = ws.totals[TOT_CHUNKS];
-    const uint32_t per = (nChunks + gridDim.x - 1) / gridDim.x;
-    const uint32_t cBeg = blockIdx.x * per, cEnd = min(nChunks, cBeg + per);
+    const uint32_t cBeg = (uint32_t)((unsigned long long)nChunks * blockIdx.x / gridDim.x);
+    const uint32_t cEnd = (uint32_t)((unsigned long long)nChunks * (blockIdx.x + 1) / gridDim.x);
     const uint32_t tabLane = enc_smem_addr(sm.tab) + 8 * (lane & 15), stageA = enc_smem_addr(sm.stage);
-    uint32_t curSeg = 0xFFFFFFFFu, group = 4;
-    for (uint32_t chunk = cBeg; chunk < cEnd; chunk++) {
-        if (ws.chunkSlow[chunk]) continue;              // k_encode_slow's
-        const uint32_t s = ws.chunkSeg[chunk];
-        const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
-        if (si[SI_W] == 0) continue;                    // single-symbol stream: zero bits (mc:859)
-        if (s != curSeg) {
-            group = si[SI_MAXLEN] <= 8 ? 4u : si[SI_MAXLEN] <= 16 ? 2u : 1u;
-            __syncthreads();
-            const uint32_t e = ws.segTab[(size_t)s * 256 + tid];         // ENC_THREADS == 256 symbols; code | 1<<len
-            const uint32_t len = e ? (uint32_t)(31 - __clz(e)) : 0u;
-            const unsigned long long ent = (unsigned long long)(e ? (e ^ (1u << len)) : 0u) | ((unsigned long long)len << 32);
+    const uint32_t symA = enc_smem_addr(sm.sym), mbarA = enc_smem_addr(&sm.mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbarA) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t curSeg = 0xFFFFFFFFu, pfChunk = 0xFFFFFFFFu, phase = 0;
+    for (uint32_t base = cBeg; base < cEnd; base += ENC_DESC_BATCH) {
+        const uint32_t nb = min((uint32_t)ENC_DESC_BATCH, cEnd - base);
+        __syncthreads();                                // everyone is done with the previous batch of descriptors
+        if ((uint32_t)tid < nb) sm.desc[tid] = ws.chunkDesc[base + tid];
+        __syncthreads();
+        uint32_t i = 0;
+        while (i < nb && ((sm.desc[i].y >> CD_SKIP_SHIFT) & 1u)) i++;
+        while (i < nb) {
+            const uint4 d = sm.desc[i];
+            uint32_t j = i + 1;                         // the next chunk that is ours
+            while (j < nb && ((sm.desc[j].y >> CD_SKIP_SHIFT) & 1u)) j++;
+            const uint32_t cnt = d.y & CD_CNT_MASK, group = (d.y >> CD_GROUP_SHIFT) & 7u, s = d.y >> CD_SEG_SHIFT;
+            const uint8_t *src = ws.strm[(d.y >> CD_K_SHIFT) & 3u] + d.x;
+            const unsigned long long gb0 = (unsigned long long)d.z | ((unsigned long long)d.w << 32);
+            // first chunk of a batch: nobody fetched it ahead (all threads are past the previous scan barrier)
+            if (pfChunk != base + i && tid == 0 && cnt >= ENC_RUN) enc_bulk_fetch(symA, mbarA, src, (cnt / ENC_RUN) * ENC_RUN);
+            if (s != curSeg) {
+                const uint32_t e = ws.segTab[(size_t)s * 256 + tid];         // ENC_THREADS == 256 symbols; code | 1<<len
+                const uint32_t len = e ? (uint32_t)(31 - __clz(e)) : 0u;
+                const unsigned long long ent = (unsigned long long)(e ? (e ^ (1u << len)) : 0u) | ((unsigned long long)len << 32);
+                __syncthreads();                        // ragged-tail reader of the previous stream is done with the table
 #pragma unroll 4
-            for (int c = 0; c < 16; c++) sm.tab[tid * 16 + ((c + lane) & 15)] = ent;
-            curSeg = s;
-            __syncthreads();
-        }
-        const uint32_t b = s >> 2, k = s & 3;
-        const uint32_t c = chunk - si[SI_FIRST_CHUNK];
-        const uint32_t S = si[SI_S];
-        const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
-        const uint8_t *src = ws.strm[k] + (size_t)b * ws.strmStride[k] + (size_t)c * kChunkSyms;
-        const unsigned long long gb0 = ws.segBitBase[s] + ws.chunkBitOff[chunk];
-        const uint32_t fullBits = group == 4   ? enc_fast_chunk<4>(sm, out32, src, cnt, gb0, tabLane, stageA)
-                                  : group == 2 ? enc_fast_chunk<2>(sm, out32, src, cnt, gb0, tabLane, stageA)
-                                               : enc_fast_chunk<1>(sm, out32, src, cnt, gb0, tabLane, stageA);
-        // ---- ragged end of the stream (< 32 symbols): serial append ---------------------------
-        const uint32_t nRuns = cnt / ENC_RUN;
-        if (tid == 0 && cnt > nRuns * ENC_RUN) {
-            unsigned long long bp = gb0 + fullBits;
-            for (uint32_t i = nRuns * ENC_RUN; i < cnt; i++) {
-                const unsigned long long e = sm.tab[(uint32_t)src[i] * 16];
-                const unsigned long long v = (e & 0xFFFFFFFFull) << (bp & 31);
-                if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
-                if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
-                bp += (uint32_t)(e >> 32);
+                for (int c = 0; c < 16; c++) sm.tab[tid * 16 + ((c + lane) & 15)] = ent;
+                curSeg = s;
+                __syncthreads();
             }
+            const uint8_t *nextSrc = nullptr;
+            uint32_t nextRuns = 0;
+            if (j < nb) {
+                const uint4 dn = sm.desc[j];
+                nextSrc = ws.strm[(dn.y >> CD_K_SHIFT) & 3u] + dn.x;
+                nextRuns = (dn.y & CD_CNT_MASK) / ENC_RUN;
+                pfChunk = base + j;
+            }
+            const uint32_t fullBits =
+                group == 4   ? enc_fast_chunk<4>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns)
+                : group == 3 ? enc_fast_chunk<3>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns)
+                : group == 2 ? enc_fast_chunk<2>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns)
+                             : enc_fast_chunk<1>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns);
+            if (cnt >= ENC_RUN) phase ^= 1u;            // one completed bulk copy per chunk that has a full run
+            // ---- ragged end of the stream (< 32 symbols): serial append ---------------------------
+            const uint32_t nRuns = cnt / ENC_RUN;
+            if (tid == 0 && cnt > nRuns * ENC_RUN) {
+                unsigned long long bp = gb0 + fullBits;
+                for (uint32_t t = nRuns * ENC_RUN; t < cnt; t++) {
+                    const unsigned long long e = sm.tab[(uint32_t)src[t] * 16];
+                    const unsigned long long v = (e & 0xFFFFFFFFull) << (bp & 31);
+                    if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
+                    if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
+                    bp += (uint32_t)(e >> 32);
+                }
+            }
+            // no barrier here: the scan barrier of the next chunk orders this copy-out before the next
+            // pack, and warpBits / warpTail are rewritten only after barriers every thread has passed
+            i = j;
         }
-        // no barrier here: the scan barrier of the next chunk orders this copy-out before the next
-        // pack, and warpBits / warpTail are rewritten only after barriers every thread has passed
     }
 }
 
@@ -828,7 +920,10 @@ k_headers(Ws ws, uint8_t *__restrict__ out, uint32_t nBlocks, uint32_t withHeade
 // =========================================================================================
 // launches
 // =========================================================================================
-void huff_init() {}
+void huff_init()
+{
+    cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncFastSmem));
+}
 
 int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
                       uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
@@ -845,15 +940,16 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     k_tree<<<nSeg, 256, 0, st>>>(ws, nSeg); launches++;
     if (mark) mark(markArg, 4);
     k_chunk_bits<<<numSM * 4, 256, 0, st>>>(ws); launches++;
-    k_seg_scan<<<(nSeg + 255) / 256, 256, 0, st>>>(ws, nSeg); launches++;
     k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, withHeader, outCap); launches++;
+    k_seg_scan<<<(nSeg + 255) / 256, 256, 0, st>>>(ws, nSeg); launches++;
     if (mark) mark(markArg, 5);
-    k_encode<<<numSM * 4, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
-    k_encode_slow<<<numSM * 2, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
+    k_encode<<<numSM * 4, ENC_THREADS, sizeof(EncFastSmem), st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
     if (mark) mark(markArg, 6);
+    k_encode_slow<<<numSM * 2, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
+    if (mark) mark(markArg, 7);
     k_headers<<<(nBlocks + 3) / 4, 128, 0, st>>>(ws, out, nBlocks, withHeader, hdrTotalBytes, hdrBlocks, batchStartCursor);
     launches++;
-    if (mark) mark(markArg, 7);
+    if (mark) mark(markArg, 8);
     return launches;
 }
 
