@@ -166,28 +166,36 @@ k_tree(Ws ws, uint32_t nSeg)
     const uint32_t base = 512 - R;                           // mc:569: first internal node index
 
     if (t == 0 && R >= 2) {
-        // ---- two-queue merge (mc:575-607): on equal weight a leaf, then the older internal node, goes first
+        // ---- two-queue merge (mc:575-607): on equal weight a leaf, then the older internal node, goes first.
+        // The two front weights of either queue live in registers (an exhausted queue reads as INF; real
+        // weights are at most 2^20), so the serial chain per pop is a compare and a few moves: the shared
+        // loads that refill the look-ahead and the stores that record the tree are off the critical path.
+        constexpr uint32_t INF = 0xFFFFFFFFu;
         uint32_t qa = 0, qb = 0, made = 0;
+        uint32_t a0 = sm.sw[0], a1 = sm.sw[1];               // R >= 2
+        uint32_t b0 = INF, b1 = INF;
         while ((R - qa) + (made - qb) > 1) {
             uint32_t sum = 0;
 #pragma unroll
             for (int side = 0; side < 2; side++) {
-                bool leaf;
-                if (qa >= R) leaf = false;
-                else if (qb >= made) leaf = true;
-                else leaf = sm.sw[qa] <= sm.iw[qb];
-                if (leaf) {
+                if (a0 <= b0) {                              // leaf (both queues cannot be empty here)
                     const uint32_t sym = sm.ssym[qa];
                     sm.child[2 * made + side] = (uint16_t)sym;
                     sm.parLeaf[sym] = (uint16_t)(2 * made + side);
-                    sum += sm.sw[qa]; qa++;
+                    sum += a0; qa++;
+                    a0 = a1;
+                    a1 = qa + 1 < R ? sm.sw[qa + 1] : INF;
                 } else {
                     sm.child[2 * made + side] = (uint16_t)(base + qb);
                     sm.parInt[qb] = (uint16_t)(2 * made + side);
-                    sum += sm.iw[qb]; qb++;
+                    sum += b0; qb++;
+                    b0 = b1;
+                    b1 = qb + 1 < made ? sm.iw[qb + 1] : INF;
                 }
             }
             sm.iw[made] = sum;
+            if (qb == made) b0 = sum;                        // the new node is the front of its queue
+            else if (qb + 1 == made) b1 = sum;               // or the one right behind the front
             made++;
         }
         sm.parInt[Tn - 1] = 0xFFFF;                          // root
