@@ -292,33 +292,50 @@ constexpr int CD_SEG_SHIFT = 20;              // stream id b*4+k (< 4096)
 __global__ void __launch_bounds__(256)
 k_seg_scan(Ws ws, uint32_t nSeg)
 {
-    const uint32_t s = blockIdx.x * 256 + threadIdx.x;
+    // one warp per stream: 32 chunks per trip, warp prefix sum of their bit lengths
+    const int lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (s >= nSeg) return;
     const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
     const uint32_t first = si[SI_FIRST_CHUNK], nch = si[SI_NCHUNKS], S = si[SI_S], W = si[SI_W];
     const uint32_t maxlen = si[SI_MAXLEN];
-    uint32_t off = 0, slow = 0;
     const bool longCodes = maxlen > 24;                      // fast path keeps a code in 24 bits (GROUP 1) or merges 2..4 into 32
     const uint32_t group = maxlen <= 8 ? 4u : maxlen <= 10 ? 3u : maxlen <= 16 ? 2u : 1u;
     const uint32_t b = s >> 2, k = s & 3;
     const unsigned long long bitBase = ws.segBitBase[s];
     const uint32_t arena = b * ws.strmStride[k];
-    for (uint32_t c = 0; c < nch; c++) {
-        const uint32_t bits = ws.chunkBits[first + c];
-        ws.chunkBitOff[first + c] = off;
-        const bool sl = W != 0 && (longCodes || bits > kEncStageBits - 128);   // does not fit the stage at any alignment
-        ws.chunkSlow[first + c] = sl ? 1 : 0;
-        slow += sl ? 1u : 0u;
-        const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
-        const unsigned long long gb0 = bitBase + off;
-        const uint32_t skip = (sl || W == 0) ? 1u : 0u;
-        ws.chunkDesc[first + c] = make_uint4(arena + c * kChunkSyms,
-                                             cnt | (k << CD_K_SHIFT) | (group << CD_GROUP_SHIFT) | (skip << CD_SKIP_SHIFT) | (s << CD_SEG_SHIFT),
-                                             (uint32_t)gb0, (uint32_t)(gb0 >> 32));
-        off += bits;
+    uint32_t running = 0, slow = 0;
+    for (uint32_t c0 = 0; c0 < nch; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const bool have = c < nch;
+        const uint32_t bits = have ? ws.chunkBits[first + c] : 0u;
+        uint32_t inc = bits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const uint32_t off = running + inc - bits;
+        if (have) {
+            ws.chunkBitOff[first + c] = off;
+            const bool sl = W != 0 && (longCodes || bits > kEncStageBits - 128);   // does not fit the stage at any alignment
+            ws.chunkSlow[first + c] = sl ? 1 : 0;
+            slow += sl ? 1u : 0u;
+            const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
+            const unsigned long long gb0 = bitBase + off;
+            const uint32_t skip = (sl || W == 0) ? 1u : 0u;
+            ws.chunkDesc[first + c] = make_uint4(arena + c * kChunkSyms,
+                                                 cnt | (k << CD_K_SHIFT) | (group << CD_GROUP_SHIFT) | (skip << CD_SKIP_SHIFT) | (s << CD_SEG_SHIFT),
+                                                 (uint32_t)gb0, (uint32_t)(gb0 >> 32));
+        }
+        running += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
-    if (slow) atomicAdd(&ws.totals[TOT_SLOW], slow);
-    if (nch && ((off + 31) >> 5) != W) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_INTERNAL);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) slow += __shfl_xor_sync(0xFFFFFFFFu, slow, d);
+    if (lane == 0) {
+        if (slow) atomicAdd(&ws.totals[TOT_SLOW], slow);
+        if (nch && ((running + 31) >> 5) != W) atomicOr(&ws.totals[TOT_ERR], (uint32_t)E_INTERNAL);
+    }
 }
 
 // =========================================================================================
@@ -949,7 +966,7 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     if (mark) mark(markArg, 4);
     k_chunk_bits<<<numSM * 4, 256, 0, st>>>(ws); launches++;
     k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, withHeader, outCap); launches++;
-    k_seg_scan<<<(nSeg + 255) / 256, 256, 0, st>>>(ws, nSeg); launches++;
+    k_seg_scan<<<(nSeg + 7) / 8, 256, 0, st>>>(ws, nSeg); launches++;
     if (mark) mark(markArg, 5);
     k_encode<<<numSM * 4, ENC_THREADS, sizeof(EncFastSmem), st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
     if (mark) mark(markArg, 6);
