@@ -348,6 +348,14 @@ __device__ __forceinline__ uint32_t section_bytes(const uint32_t *si)
     if (si[SI_RAW]) return S;
     return si[SI_HDR] + 4 + 4 * si[SI_W];
 }
+static_assert(SI_WORDS == 8, "a segInfo row is read as two 16-byte vectors");
+// the same from a row held in registers (lo = words 0..3, hi = words 4..7)
+__device__ __forceinline__ uint32_t section_bytes(const uint4 &lo, const uint4 &hi)
+{
+    if (lo.x == 0) return 0;                 // SI_S
+    if (hi.z) return lo.x;                   // SI_RAW
+    return lo.z + 4 + 4 * lo.w;              // SI_HDR + 4 + 4 * SI_W
+}
 
 __global__ void __launch_bounds__(1024)
 k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
@@ -364,19 +372,27 @@ k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
     for (uint32_t base = 0; base < nBlocks; base += 1024) {
         const uint32_t b = base + tid;
         unsigned long long rec = 0;
-        uint32_t sec[4] = {0, 0, 0, 0};
+        uint32_t sec[4] = {0, 0, 0, 0}, hdrB[4] = {0, 0, 0, 0};
         if (b < nBlocks) {
+            // the block's four segInfo rows: eight independent 16-byte loads, one round trip
+            uint4 lo[4], hi[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint4 *row = reinterpret_cast<const uint4 *>(ws.segInfo + ((size_t)b * 4 + k) * SI_WORDS);
+                lo[k] = row[0]; hi[k] = row[1];
+            }
+            const uint32_t T = ws.meta[(size_t)b * M_WORDS + M_T], Pc = ws.meta[(size_t)b * M_WORDS + M_PC];
             unsigned long long sin = 0, sout = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t *si = ws.segInfo + ((size_t)b * 4 + k) * SI_WORDS;
-                sec[k] = section_bytes(si);
-                if (si[SI_W]) { sin += si[SI_S]; sout += 4ull * si[SI_W]; }
+                sec[k] = section_bytes(lo[k], hi[k]);
+                hdrB[k] = lo[k].z;
+                if (lo[k].w) { sin += lo[k].x; sout += 4ull * lo[k].w; }
             }
             rec = 4ull + 4 + sec[0] + sec[1] + 4 + sec[2] + 4 + sec[3];   // u32 size | payload (mc:4111-4114)
             atomicAdd(&accSin, sin); atomicAdd(&accSout, sout);
-            atomicAdd(&accTok, (unsigned long long)ws.meta[(size_t)b * M_WORDS + M_T]);
-            atomicAdd(&accMat, (unsigned long long)ws.meta[(size_t)b * M_WORDS + M_PC]);
+            atomicAdd(&accTok, (unsigned long long)T);
+            atomicAdd(&accMat, (unsigned long long)Pc);
         }
         unsigned long long inc = rec;
 #pragma unroll
@@ -393,10 +409,10 @@ k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
             ws.blkOff[b] = off;
             // absolute bit position of word 0 of each stream's code words
             unsigned long long p = off + 4 + 4;                                  // size, T
+#pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t *si = ws.segInfo + ((size_t)b * 4 + k) * SI_WORDS;
                 if (k == 2 || k == 3) p += 4;                                    // Pc before p section, G before Golomb section
-                ws.segBitBase[(size_t)b * 4 + k] = 8ull * (p + si[SI_HDR] + 4);
+                ws.segBitBase[(size_t)b * 4 + k] = 8ull * (p + hdrB[k] + 4);
                 p += sec[k];
             }
         }
