@@ -126,6 +126,29 @@ def test_huffman_section_bytes(dc):
         assert got == want, "%s: section differs at byte %d of %d/%d" % (name, _first_diff(got, want), len(got), len(want))
 
 
+def test_huffman_encode_groups_and_chunk_edges(dc):
+    """k_encode picks 4 / 3 / 2 / 1 symbols per 32-bit insert by the stream's longest code (<= 8 / 10 /
+    16 / 24 bits; longer goes to k_encode_slow): Fibonacci weights over m symbols give a longest code
+    of m-1 bits.  Lengths sit around the 32-symbol run and 8192-symbol chunk boundaries, where the
+    ragged tail, the bulk-copy size and the descriptor batch change behaviour."""
+    o = oracle()
+    rng = np.random.default_rng(77)
+    for m in (2, 9, 10, 11, 12, 17, 18, 25, 26, 28):
+        fib = [1, 1]
+        while len(fib) < m:
+            fib.append(fib[-1] + fib[-2])
+        base = rng.permutation(np.repeat(np.arange(m, dtype=np.uint8) * 7 + 3, fib))
+        while len(base) < 8192 * 3 + 40:                      # short multisets: repeat (the weights keep their ratios)
+            base = np.concatenate([base, rng.permutation(base)])
+        F = min(len(base), 1 << 20)
+        sizes = {F, F - 1, 31, 32, 33, 63, 8191, 8192, 8193, 8192 + 31, 8192 * 2 + 32, 8192 * 3 + 1}
+        for n in sorted(x for x in sizes if 0 < x <= F):
+            s = np.ascontiguousarray(base[:n])
+            want = o.huffman_section(s)
+            got = dc.probe_huffman_section(_dev(s))
+            assert got == want, "m=%d n=%d: section differs at byte %d of %d/%d" % (m, n, _first_diff(got, want), len(got), len(want))
+
+
 def test_block_payloads_vs_oracle_and_golden():
     o = oracle()
     for name, buf in small_buffers(seed=2024):
