@@ -137,6 +137,13 @@ def compress(data, n_gpus=1):
     return out[: n.value].tobytes()
 
 
+def decompress_into(src, dst, n_gpus=1):
+    """FCX7 container (numpy uint8) -> decoded bytes written into ``dst`` (numpy uint8, ideally pinned); returns byte count."""
+    n = C.c_uint64(0)
+    _check(lib().fcx_decompress_lz77(src.ctypes.data, src.size, dst.ctypes.data, dst.size, C.byref(n), device_mask(n_gpus)))
+    return int(n.value)
+
+
 def decompress(blob, n_gpus=1):
     """``./my_compress -i in -o out`` on a buffer: what the reference's decoder writes."""
     x = _host_u8(blob)

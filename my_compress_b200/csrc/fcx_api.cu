@@ -353,6 +353,9 @@ struct DevSlot {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     std::vector<cudaEvent_t> evIn, evOut;   // per sub-batch
     uint64_t *hostCursor = nullptr;         // pinned, per sub-batch
+    // decoder scratch (grow-only)
+    uint8_t *decScratch = nullptr; uint64_t decScratchCap = 0;
+    uint64_t *decRec = nullptr; uint32_t *decLen = nullptr; uint32_t decBlocks = 0;
 };
 DevSlot g_slots[64];
 constexpr uint32_t kMaxPipeBatches = 64;
@@ -540,37 +543,51 @@ static int decode_on_device(int dev, const uint8_t *file, uint64_t nbytes, const
     DevSlot &s = g_slots[dev];
     std::lock_guard<std::mutex> lk(s.mu);
     const uint32_t nb = (uint32_t)recOff.size();
-    const uint64_t rawCap = (uint64_t)nb * (kBlockBytes + 8);
+    const uint64_t rawCap = (uint64_t)nb * kBlockBytes + 16;       // block b decodes to dOut + b MiB
     int rc = slot_prepare(s, dev, nbytes + 16, rawCap);
     if (rc) return rc;
     fcx_ctx *c = s.ctx;
-    uint8_t *scratch = nullptr; uint64_t *dRec = nullptr; uint32_t *dLen = nullptr;
     const size_t per = decode_scratch_per_block();
-    CK(cudaMalloc(&scratch, per * nb + 256));
-    CK(cudaMalloc(&dRec, sizeof(uint64_t) * (nb + 1)));
-    CK(cudaMalloc(&dLen, sizeof(uint32_t) * (nb + 1)));
-    auto cleanup = [&]() { cudaFree(scratch); cudaFree(dRec); cudaFree(dLen); };
-    cudaError_t e = cudaMemcpyAsync(s.dIn, file, nbytes, cudaMemcpyHostToDevice, s.stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(s.dIn + nbytes, 0, 16, s.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dRec, recOff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s.stream);
-    if (e != cudaSuccess) { cleanup(); return fail(FCX_ERR_CUDA, cudaGetErrorString(e)); }
-    c->launches += launch_decode(s.dIn, dRec, nb, s.dOut, dLen, scratch, per, s.stream);
-    std::vector<uint32_t> lens(nb);
-    e = cudaMemcpyAsync(lens.data(), dLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, s.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-    if (e != cudaSuccess) { cleanup(); return fail(FCX_ERR_CUDA, cudaGetErrorString(e)); }
-    uint64_t at = 0;
-    for (uint32_t b = 0; b < nb; b++) {
-        if (lens[b] == 0xFFFFFFFFu) { cleanup(); return fail(FCX_ERR_FORMAT, "corrupt block payload"); }
-        if (at + lens[b] > outCap) { cleanup(); return fail(FCX_ERR_CAPACITY, "output buffer too small"); }
-        e = cudaMemcpyAsync(out + at, s.dOut + (uint64_t)b * (kBlockBytes + 8), lens[b], cudaMemcpyDeviceToHost, s.stream);
-        if (e != cudaSuccess) { cleanup(); return fail(FCX_ERR_CUDA, cudaGetErrorString(e)); }
-        at += lens[b];
+    if (s.decScratchCap < per * nb) {
+        if (s.decScratch) cudaFree(s.decScratch);
+        s.decScratch = nullptr; s.decScratchCap = 0;
+        CK(cudaMalloc(&s.decScratch, per * nb + 256));
+        s.decScratchCap = per * nb;
     }
-    e = cudaStreamSynchronize(s.stream);
-    cleanup();
-    if (e != cudaSuccess) return fail(FCX_ERR_CUDA, cudaGetErrorString(e));
-    *outN = at;
+    if (s.decBlocks < nb) {
+        if (s.decRec) cudaFree(s.decRec);
+        if (s.decLen) cudaFree(s.decLen);
+        s.decRec = nullptr; s.decLen = nullptr; s.decBlocks = 0;
+        CK(cudaMalloc(&s.decRec, sizeof(uint64_t) * (nb + 1)));
+        CK(cudaMalloc(&s.decLen, sizeof(uint32_t) * (nb + 1)));
+        s.decBlocks = nb;
+    }
+    CK(cudaMemcpyAsync(s.dIn, file, nbytes, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemsetAsync(s.dIn + nbytes, 0, 16, s.stream));
+    CK(cudaMemcpyAsync(s.decRec, recOff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s.stream));
+    c->launches += launch_decode(s.dIn, s.decRec, nb, s.dOut, s.decLen, s.decScratch, per, s.stream);
+    std::vector<uint32_t> lens(nb);
+    CK(cudaMemcpyAsync(lens.data(), s.decLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    uint64_t total = 0;
+    bool packed = true;                                            // every block but the last is full: one copy
+    for (uint32_t b = 0; b < nb; b++) {
+        if (lens[b] == 0xFFFFFFFFu) return fail(FCX_ERR_FORMAT, "corrupt block payload");
+        if (b + 1 < nb && lens[b] != kBlockBytes) packed = false;
+        total += lens[b];
+    }
+    if (total > outCap) return fail(FCX_ERR_CAPACITY, "output buffer too small");
+    if (packed) {
+        if (total) CK(cudaMemcpyAsync(out, s.dOut, total, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+        uint64_t at = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+            if (lens[b]) CK(cudaMemcpyAsync(out + at, s.dOut + (uint64_t)b * kBlockBytes, lens[b], cudaMemcpyDeviceToHost, s.stream));
+            at += lens[b];
+        }
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    *outN = total;
     return FCX_OK;
 }
 

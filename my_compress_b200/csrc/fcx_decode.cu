@@ -6,22 +6,19 @@
 // reference produces, including a single-symbol stream decoding to zeros
 // and the "Fatal Error" early stop when matches run out (mc:2337-2340).
 //
-// The format has no resynchronisation points, so a Huffman section and the Golomb stream can
-// only be read front to back; the parallelism is across blocks (one CTA each, ~7 CTAs per SM,
-// so ~1000 blocks decode at once) and across the four sections of a block (one warp each):
-//   * every warp builds an 11-bit look-up table of its tree in shared memory (an entry holds
-//     up to three symbols whose codes fit the window) and decodes warp-uniformly: all lanes
-//     carry the same bit buffer, code words are fetched 32 at a time with one coalesced load and
-//     handed out by shuffle, a slow bit-by-bit walk takes over for long codes and at the ends;
-//   * the warp of the Golomb section then parses the l values the same way (count the ones
-//     with one ffs, two remainder bits);
-//   * warp 0 replays the tokens 32 at a time: flag bits -> match ranks (popc), a warp scan of
-//     len+1 gives every token its output position, tokens whose source lies before the batch copy
-//     in parallel inside a 16 KB shared ring of recent output, the few that reach into the
-//     batch follow in order (overlapping copies use source offset k mod p), and finished words
-//     are flushed to HBM with coalesced stores.
+// The format has no resynchronisation points, so the sequential dependency of a prefix-coded
+// stream is broken speculatively (see spec_decode): one CTA per block, its 128 lanes decode
+// the four Huffman sections one after the other (11-bit look-up table in shared memory, tree
+// walk for longer codes), then the Golomb stream of l values with the same scheme.  All lanes then
+// gather 1024 tokens at a time into shared memory (flag bits -> match ranks by popc and a scan)
+// and warp 0 replays them 32 per trip: a warp scan of len+1 gives every token its output
+// position, tokens whose source lies before the batch copy in parallel
+// inside a 16 KB shared ring of recent output, the few that reach into the batch follow in
+// order (overlapping copies use source offset k mod p), and finished words are flushed to HBM
+// with coalesced stores.
 // Malformed payloads that would send the reference out of bounds yield length 0xFFFFFFFF;
-// a match length above 257 (the encoder's maximum) or a distance of 0 is treated as malformed.
+// a match length above 257 (the encoder's maximum), a distance of 0 or a block that would decode to more
+// than 1 MiB (the reference tolerates 8 bytes more) is treated as malformed.
 #include "fcx_dev.cuh"
 
 namespace fcx {
@@ -38,20 +35,27 @@ static_assert(DEC_SCRATCH % 16 == 0 && DEC_OFF_LV % 16 == 0, "scratch regions st
 
 size_t decode_scratch_per_block() { return DEC_SCRATCH; }
 
+constexpr int DEC_THREADS = 128;
 constexpr int DEC_LUT_BITS = 11;
 constexpr int DEC_LUT = 1 << DEC_LUT_BITS;
 constexpr uint32_t DEC_RING = 16384;                              // >= 2047 (window) + 32 * 258 (one batch)
-constexpr uint32_t DEC_LUT_INVALID = 0xFFFFFFFFu;
+constexpr uint32_t DEC_SUB_BITS = 512;                            // bits a lane decodes per trip
+constexpr uint32_t DEC_FIN = 0xFFFFFFFFu;                         // "the stream ended inside this subsequence"
+constexpr int DEC_SUPER = 8 * DEC_THREADS;                        // tokens gathered per trip
+constexpr uint32_t DEC_TOK_NONE = 0xFFFD, DEC_TOK_STOP = 0xFFFE, DEC_TOK_BAD = 0xFFFF;
 
 struct DecSmem {
-    union {
-        uint32_t lut[4][DEC_LUT];        // phase 1: bits 0-3 code bits used, 4-5 symbols, 8.. up to three symbols
-        uint8_t ring[DEC_RING];          // phase 2: the most recent output bytes, addressed by position & (DEC_RING-1)
-    };
-    uint8_t pair[4][512];
-    uint8_t map[4][64];
+    uint8_t ring[DEC_RING];              // replay: the most recent output bytes, addressed by position & (DEC_RING-1)
+    uint16_t lut[DEC_LUT];               // current section: len << 8 | symbol for codes of <= 11 bits, else 0
+    uint8_t pair[512];
+    uint8_t map[64];
+    uint32_t endS[DEC_THREADS];          // bit position at which each lane's subsequence ends (DEC_FIN: stream over)
+    uint32_t warpTot[DEC_THREADS / 32];
     uint32_t secOff[4], secCnt[4], secTn[4], secW[4], secRaw[4];
-    uint32_t T, Pc, G, bad, nL;
+    uint32_t T, Pc, G, bad, nL, fin;
+    uint16_t tokL[DEC_SUPER];            // replay: match length per token (0 literal-only), or a DEC_TOK_* marker
+    uint16_t tokP[DEC_SUPER];            //         distance
+    uint8_t tokC[DEC_SUPER];             //         literal byte
 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p)
@@ -74,175 +78,160 @@ __device__ uint32_t parse_section(DecSmem &sm, int k, const uint8_t *pl, uint32_
     return wAt + 4 + 4 * W;
 }
 
-// ---- warp-uniform reader of little-endian 32-bit words at any byte address --------------------
-// Every lane holds the same state; words come 32 at a time (lane i loads word base+i, the next
-// 32 are requested while the current ones are consumed) and are broadcast by shuffle.
-struct BitReader {
-    const uint32_t *aligned;     // base rounded down to 4 bytes
-    uint32_t sh;                 // (address & 3) * 8
-    uint32_t W;                  // words in the stream
-    uint32_t wi;                 // next word to hand out
-    uint32_t curW, nextW;        // this lane's word of the current / next group of 32
+// ---- per-lane bit cursor over little-endian 32-bit words at any byte address -------------------
+template <bool kConst>
+struct LaneBits {
+    const uint32_t *a;           // base rounded down to 4 bytes
+    uint32_t sh, W;              // (address & 3) * 8, words in the stream
+    uint32_t wi, nbits, pos;     // next word, valid bits in buf, bit index of buf's bit 0
     unsigned long long buf;
-    uint32_t nbits;
-
-    __device__ __forceinline__ uint32_t load_word(uint32_t i) const
+    __device__ __forceinline__ uint32_t ld(const uint32_t *p) const { return kConst ? __ldg(p) : __ldcg(p); }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const
     {
-        if (i >= W) return 0u;
-        const uint32_t a0 = __ldcg(aligned + i);
-        if (sh == 0) return a0;
-        return __funnelshift_r(a0, __ldcg(aligned + i + 1), sh);
+        const uint32_t w0 = ld(a + i);
+        return sh ? __funnelshift_r(w0, ld(a + i + 1), sh) : w0;
     }
-    __device__ __forceinline__ void init(const uint8_t *p, uint32_t words)
+    __device__ __forceinline__ void open(const uint8_t *p, uint32_t words)
     {
-        const int lane = threadIdx.x & 31;
-        aligned = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+        a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
         sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-        W = words; wi = 0; buf = 0; nbits = 0;
-        curW = load_word(lane);
-        nextW = load_word(32 + lane);
+        W = words; wi = 0; nbits = 0; pos = 0; buf = 0;
     }
-    // appends one word to the bit buffer (call only when nbits <= 32); false when the stream is exhausted
-    __device__ __forceinline__ bool refill()
+    __device__ __forceinline__ void seek(uint32_t bit)
     {
-        if (wi >= W) return false;
-        const uint32_t w = __shfl_sync(0xFFFFFFFFu, curW, wi & 31);
-        buf |= (unsigned long long)w << nbits;
-        nbits += 32;
-        wi++;
-        if ((wi & 31) == 0) {
-            curW = nextW;
-            nextW = load_word(wi + 32 + (threadIdx.x & 31));
-        }
-        return true;
+        pos = bit; wi = bit >> 5; buf = 0; nbits = 0;
+        if (wi < W) { buf = word(wi) >> (bit & 31); nbits = 32 - (bit & 31); wi++; }
     }
+    __device__ __forceinline__ void fill()
+    {
+        if (nbits <= 32 && wi < W) { buf |= (unsigned long long)word(wi) << nbits; nbits += 32; wi++; }
+    }
+    __device__ __forceinline__ void skip(uint32_t n) { buf >>= n; nbits -= n; pos += n; }       // n < 64
+    __device__ __forceinline__ void drop_all() { pos += nbits; buf = 0; nbits = 0; }
 };
 
-// packed byte writer: symbols are collected four at a time and stored as one word by lane 0
-struct ByteWriter {
-    uint32_t *dst32;
-    unsigned long long acc;
-    uint32_t have;               // bytes waiting in acc
-    uint32_t j;                  // bytes produced so far
-    __device__ __forceinline__ void init(uint8_t *dst) { dst32 = reinterpret_cast<uint32_t *>(dst); acc = 0; have = 0; j = 0; }
-    __device__ __forceinline__ void put(uint32_t syms, uint32_t n)
+// next(): 0 = one symbol decoded, 1 = the stream ended first, 2 = malformed tree
+struct HuffCodec {
+    const uint16_t *lut;
+    const uint8_t *pairK, *mapK;
+    uint32_t Tn, R, root;
+    template <class B>
+    __device__ __forceinline__ int next(B &lb, uint32_t &sym) const
     {
-        acc |= (unsigned long long)syms << (8 * have);
-        have += n; j += n;
-        if (have >= 4) {
-            if ((threadIdx.x & 31) == 0) dst32[(j - have) >> 2] = (uint32_t)acc;
-            acc >>= 32; have -= 4;
-        }
-    }
-    __device__ __forceinline__ void finish()      // buffers are zero-filled and padded: a whole word is fine
-    {
-        if (have && (threadIdx.x & 31) == 0) dst32[(j - have) >> 2] = (uint32_t)acc;
-    }
-};
-
-// One Huffman section, decoded by a whole warp (uniformly).  Returns false on a malformed tree.
-__device__ bool decode_section(DecSmem &sm, int k, const uint8_t *pl, uint8_t *dst)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t at = sm.secOff[k], cnt = sm.secCnt[k], Tn = sm.secTn[k], W = sm.secW[k];
-    if (sm.secRaw[k]) {
-        for (uint32_t i = lane; i < cnt; i += 32) dst[i] = pl[at + i];
-        return true;
-    }
-    // Tn == 0 (single-symbol stream): nothing is decoded, the zero-filled buffer stands (App. B1)
-    if (!(cnt && Tn && W)) return true;
-    const uint32_t mapB = (2 * Tn + 7) / 8;
-    for (uint32_t i = lane; i < mapB; i += 32) sm.map[k][i] = pl[at + 1 + i];
-    for (uint32_t i = lane; i < 2 * Tn; i += 32) sm.pair[k][i] = pl[at + 1 + mapB + i];
-    __syncwarp();
-    const uint32_t R = Tn + 1, root = Tn - 1;                        // root = last stored node (mc:945-946)
-    const uint8_t *pairK = sm.pair[k], *mapK = sm.map[k];
-    // ---- look-up table: greedy decode of the 11 index bits, up to three symbols ---------------
-    for (uint32_t idx = lane; idx < (uint32_t)DEC_LUT; idx += 32) {
-        uint32_t node = root, used = 0, ns = 0, syms = 0, e = 0;
-        for (int bit = 0; bit < DEC_LUT_BITS; bit++) {
-            const uint32_t c = 2 * node + ((idx >> bit) & 1u);
-            const uint32_t ci = pairK[c];
-            if (!((mapK[c >> 3] >> (c & 7)) & 1)) {                  // leaf (mc:968)
-                syms |= ci << (8 * ns);
-                ns++; used = bit + 1; node = root;
-                if (ns == 3) break;
-            } else {
-                node = ci - (256 - R);                               // mc:976-977
-                if (node >= Tn) { if (ns == 0) e = DEC_LUT_INVALID; break; }
-            }
-        }
-        if (e != DEC_LUT_INVALID) e = ns ? (used | (ns << 4) | (syms << 8)) : 0u;
-        sm.lut[k][idx] = e;
-    }
-    __syncwarp();
-    const uint32_t *lut = sm.lut[k];
-    BitReader br;
-    br.init(pl + at + 1 + mapB + 2 * Tn + 4, W);
-    ByteWriter bw;
-    bw.init(dst);
-    bool bad = false;
-    while (bw.j < cnt) {
-        if (br.nbits <= 32) br.refill();
-        const uint32_t e = lut[(uint32_t)br.buf & (DEC_LUT - 1)];
-        const uint32_t used = e & 15u, ns = (e >> 4) & 3u;
-        if (e != 0 && e != DEC_LUT_INVALID && used <= br.nbits && bw.j + ns <= cnt) {
-            bw.put(e >> 8, ns);
-            br.buf >>= used; br.nbits -= used;
-            continue;
-        }
-        // ---- exact path: one symbol, bit by bit (long codes, the last bits, the last symbols) ----
-        uint32_t node = root;
-        bool done = false;
+        lb.fill();
+        if (lb.nbits == 0) return 1;                                 // out of code words (mc:955)
+        const uint32_t e = lut[(uint32_t)lb.buf & (DEC_LUT - 1)];
+        const uint32_t len = e >> 8;
+        if (e && len <= lb.nbits) { sym = e & 0xFFu; lb.skip(len); return 0; }
+        uint32_t node = root;                                        // long code, or the last bits: walk the tree
         for (;;) {
-            if (br.nbits == 0 && !br.refill()) { done = true; break; }        // out of code words (mc:955)
-            const uint32_t c = 2 * node + ((uint32_t)br.buf & 1u);
-            br.buf >>= 1; br.nbits--;
+            if (lb.nbits == 0) { lb.fill(); if (lb.nbits == 0) return 1; }
+            const uint32_t c = 2 * node + ((uint32_t)lb.buf & 1u);
+            lb.skip(1);
             const uint32_t ci = pairK[c];
-            if (!((mapK[c >> 3] >> (c & 7)) & 1)) { bw.put(ci, 1); break; }
-            node = ci - (256 - R);
-            if (node >= Tn) { bad = true; done = true; break; }
+            if (!((mapK[c >> 3] >> (c & 7)) & 1)) { sym = ci; return 0; }   // leaf (mc:968)
+            node = ci - (256 - R);                                   // mc:976-977
+            if (node >= Tn) return 2;
         }
-        if (done) break;
     }
-    bw.finish();
-    return !bad;
-}
+};
 
-// golomb_rice_decode (mc:309-358) for up to Pc values: l = 4*q + r, q ones, a zero, two remainder bits.
-// Stops at the first value whose bits are not all there (the reference's overrun check); returns how
-// many values were stored.
-__device__ uint32_t parse_golomb(const uint8_t *gb, uint32_t G, uint32_t Pc, uint16_t *lv)
-{
-    const int lane = threadIdx.x & 31;
-    BitReader br;
-    br.init(gb, G);
-    uint32_t m = 0;
-    while (m < Pc) {
+// golomb_rice_decode (mc:309-358): q ones, a zero, two remainder bits -> l = 4*q + r.  A value whose
+// bits are not all there ends the stream (the reference's overrun check).
+struct GolombCodec {
+    template <class B>
+    __device__ __forceinline__ int next(B &lb, uint32_t &sym) const
+    {
         uint32_t q = 0;
-        bool ok = true;
-        for (;;) {                                                   // the run of ones
-            if (br.nbits <= 32 && !br.refill() && br.nbits == 0) { ok = false; break; }
-            const unsigned long long inv = ~br.buf;
+        for (;;) {
+            lb.fill();
+            if (lb.nbits == 0) return 1;
+            const unsigned long long inv = ~lb.buf;
             const uint32_t ones = inv ? (uint32_t)(__ffsll((long long)inv) - 1) : 64u;
-            if (ones >= br.nbits) { q += br.nbits; br.buf = 0; br.nbits = 0; continue; }   // run goes on in the next word
-            q += ones;
-            br.buf >>= ones; br.nbits -= ones;
+            if (ones >= lb.nbits) { q += lb.nbits; lb.drop_all(); continue; }   // the run goes on in the next word
+            q += ones; lb.skip(ones);
             break;
         }
-        if (!ok) break;
-        if (br.nbits < 3) br.refill();
-        if (br.nbits < 3) break;                                     // gpos + 3 > 32*G
-        const uint32_t r = ((uint32_t)br.buf >> 1) & 3u;
-        br.buf >>= 3; br.nbits -= 3;
-        const uint32_t l = min(q * 4u + r, 0xFFFFu);
-        if (lane == 0) lv[m] = (uint16_t)l;
-        m++;
+        lb.fill();
+        if (lb.nbits < 3) return 1;                                  // gpos + 3 > 32*G
+        sym = min(4u * q + (((uint32_t)lb.buf >> 1) & 3u), 0xFFFFu);
+        lb.skip(3);
+        return 0;
     }
-    return m;
+};
+
+// Speculative parallel decode of one prefix-coded stream by the whole CTA.  Every lane takes the
+// next DEC_SUB_BITS bits; lane 0 starts on a code boundary, the others guess.  A lane decodes until
+// it crosses into the next lane's bits and publishes where it ended; a lane whose predecessor ended
+// somewhere else than where it started decodes again from there, until nobody moves (prefix codes
+// fall into step after a few symbols, so this is one or two rounds; by induction over the lanes the
+// fixed point is the sequential decode whatever the data).  A scan of the symbol counts then gives
+// every lane its output offset for the writing pass.  Returns the symbols produced (<= cnt).
+template <class Codec, class Bits, class Emit>
+__device__ uint32_t spec_decode(DecSmem &sm, const Codec &cd, Bits lb, uint32_t cnt, Emit emit, bool &bad)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t totalBits = lb.W * 32u;
+    uint32_t segStart = 0, outBase = 0;
+    while (outBase < cnt && segStart < totalBits) {                  // CTA-uniform
+        const uint32_t bndNext = segStart + (uint32_t)(tid + 1) * DEC_SUB_BITS;
+        uint32_t myStart = segStart + (uint32_t)tid * DEC_SUB_BITS, myEnd = DEC_FIN, myN = 0;
+        bool myBad = false;
+        auto run = [&]() {
+            myN = 0; myBad = false;
+            if (myStart == DEC_FIN || myStart >= totalBits) { myEnd = DEC_FIN; return; }
+            lb.seek(myStart);
+            uint32_t sym;
+            while (lb.pos < bndNext) {
+                const int st = cd.next(lb, sym);
+                if (st) { myBad = st == 2; myEnd = DEC_FIN; return; }
+                myN++;
+            }
+            myEnd = lb.pos;
+        };
+        run();
+        sm.endS[tid] = myEnd;
+        for (;;) {
+            __syncthreads();
+            const uint32_t prevEnd = tid ? sm.endS[tid - 1] : segStart;
+            const bool moved = prevEnd != myStart;
+            if (!__syncthreads_or(moved)) break;                     // also: everyone has read before anyone rewrites
+            if (moved) { myStart = prevEnd; run(); sm.endS[tid] = myEnd; }
+        }
+        // ---- output offsets ------------------------------------------------------------------------
+        uint32_t inc = myN;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        if (lane == 31) sm.warpTot[warp] = inc;
+        __syncthreads();
+        uint32_t off = inc - myN, total = 0;
+#pragma unroll
+        for (int w = 0; w < DEC_THREADS / 32; w++) { const uint32_t v = sm.warpTot[w]; if (w < warp) off += v; total += v; }
+        const uint32_t first = outBase + off;
+        // the sequential decoder would walk into this lane's malformed code unless cnt stops it earlier
+        if (myBad && first + myN < cnt) bad = true;
+        // ---- writing pass: the same symbols again, now with a place to go ------------------------------
+        if (myN && first < cnt) {
+            const uint32_t lim = min(myN, cnt - first);
+            lb.seek(myStart);
+            uint32_t sym;
+            for (uint32_t i = 0; i < lim; i++) {
+                if (cd.next(lb, sym)) break;
+                emit(first + i, sym);
+            }
+        }
+        segStart = sm.endS[DEC_THREADS - 1];
+        outBase += total;
+        __syncthreads();                                             // endS / warpTot are rewritten by the next trip
+        if (segStart == DEC_FIN) break;
+    }
+    return min(outBase, cnt);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DEC_THREADS)
 k_decode(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff, uint8_t *__restrict__ out,
          uint32_t *__restrict__ outLen, uint8_t *__restrict__ scratchAll, size_t scratchPerBlock)
 {
@@ -254,7 +243,7 @@ k_decode(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff, 
     uint8_t *scr = scratchAll + (size_t)b * scratchPerBlock;
     uint8_t *dst[4] = {scr + DEC_OFF_BM, scr + DEC_OFF_CS, scr + DEC_OFF_PK, scr + DEC_OFF_GB};
     uint16_t *lv = reinterpret_cast<uint16_t *>(scr + DEC_OFF_LV);
-    uint8_t *o = out + (size_t)b * (kBlockBytes + 8);
+    uint8_t *o = out + (size_t)b * kBlockBytes;                    // blocks sit back to back: a full block is 1 MiB
 
     if (tid == 0) {
         sm.bad = 0; sm.Pc = 0; sm.G = 0; sm.T = 0; sm.nL = 0;
@@ -289,102 +278,178 @@ k_decode(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff, 
     __syncthreads();
     if (sm.bad) { if (tid == 0) outLen[b] = DEC_BAD; return; }
 
-    // ---- phase 1: the four sections, one warp each; the Golomb warp goes on to the l values --------
-    {
-        const bool ok = decode_section(sm, warp, pl, dst[warp]);
-        if (!ok && lane == 0) sm.bad = 1;
-        if (warp == 3) {
-            __syncwarp();
-            __threadfence_block();                                   // lane 0's stores of the Golomb bytes, read back below
-            const uint32_t nL = ok ? parse_golomb(dst[3], sm.G, sm.Pc, lv) : 0u;
-            if (lane == 0) sm.nL = nL;
+    // ---- phase 1: the four sections one after the other, all lanes on each; then the l values ------
+    for (int k = 0; k < 4; k++) {
+        __syncthreads();                                             // the previous section's table is no longer in use
+        const uint32_t at = sm.secOff[k], cnt = sm.secCnt[k], Tn = sm.secTn[k], W = sm.secW[k];
+        if (sm.secRaw[k]) {
+            for (uint32_t i = tid; i < cnt; i += DEC_THREADS) dst[k][i] = pl[at + i];
+            continue;
         }
+        // Tn == 0 (single-symbol stream): nothing is decoded, the zero-filled buffer stands (App. B1)
+        if (!(cnt && Tn && W)) continue;
+        const uint32_t mapB = (2 * Tn + 7) / 8;
+        for (uint32_t i = tid; i < mapB; i += DEC_THREADS) sm.map[i] = pl[at + 1 + i];
+        for (uint32_t i = tid; i < 2 * Tn; i += DEC_THREADS) sm.pair[i] = pl[at + 1 + mapB + i];
+        __syncthreads();
+        const uint32_t R = Tn + 1, root = Tn - 1;                    // root = last stored node (mc:945-946)
+        for (uint32_t idx = tid; idx < (uint32_t)DEC_LUT; idx += DEC_THREADS) {
+            uint32_t node = root, e = 0;
+            for (int bit = 0; bit < DEC_LUT_BITS; bit++) {
+                const uint32_t c = 2 * node + ((idx >> bit) & 1u);
+                const uint32_t ci = sm.pair[c];
+                if (!((sm.map[c >> 3] >> (c & 7)) & 1)) { e = ((uint32_t)(bit + 1) << 8) | ci; break; }
+                node = ci - (256 - R);
+                if (node >= Tn) break;                               // malformed: the exact walk reports it if it is ever reached
+            }
+            sm.lut[idx] = (uint16_t)e;
+        }
+        __syncthreads();
+        HuffCodec cd{sm.lut, sm.pair, sm.map, Tn, R, root};
+        LaneBits<true> lb;
+        lb.open(pl + at + 1 + mapB + 2 * Tn + 4, W);
+        uint8_t *d = dst[k];
+        bool bad = false;
+        spec_decode(sm, cd, lb, cnt, [d](uint32_t i, uint32_t sym) { d[i] = (uint8_t)sym; }, bad);
+        if (bad) sm.bad = 1;
     }
     __syncthreads();
     if (sm.bad) { if (tid == 0) outLen[b] = DEC_BAD; return; }
-    if (warp != 0) return;
+    {
+        uint32_t nL = 0;
+        if (sm.G && sm.Pc) {
+            GolombCodec gc;
+            LaneBits<false> gbits;
+            gbits.open(dst[3], sm.G);
+            bool bad = false;
+            nL = spec_decode(sm, gc, gbits, sm.Pc, [lv](uint32_t i, uint32_t sym) { lv[i] = (uint16_t)sym; }, bad);
+        }
+        if (tid == 0) sm.nL = nL;
+    }
+    __syncthreads();
 
-    // ---- phase 2: token replay, 32 tokens per trip (my_LZ77_decompress, mc:1716-1735) -----------------
+    // ---- phase 2: token replay (my_LZ77_decompress, mc:1716-1735) -------------------------------------
+    // 1024 tokens at a time: all lanes gather (len, distance, literal) of eight tokens each into shared
+    // memory (flag bits -> match ranks by popc and a CTA scan, then independent loads), warp 0 replays
+    // them 32 per trip.
     const uint32_t T = sm.T, Pc = sm.Pc, nL = sm.nL;
-    const uint32_t *bm32 = reinterpret_cast<const uint32_t *>(dst[0]);
-    const uint8_t *cs = dst[1], *pk = dst[2];
+    const uint8_t *bm = dst[0], *cs = dst[1], *pk = dst[2];
     uint8_t *ring = sm.ring;
     uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
     constexpr uint32_t RM = DEC_RING - 1;
-    uint32_t cur = 0, mBase = 0, flushed = 0;
-    bool bad = false, stop = false;
-    const uint32_t ltMask = (1u << lane) - 1u;
-    for (uint32_t t0 = 0; t0 < T && !stop; t0 += 32) {
-        const uint32_t t = t0 + lane;
-        bool valid = t < T;
-        const uint32_t word = __ldcg(bm32 + (t0 >> 5));
-        bool isMatch = valid && !((word >> lane) & 1u);
-        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, isMatch);
-        const uint32_t mIdx = mBase + __popc(mmask & ltMask);
-        const uint32_t stopMask = __ballot_sync(0xFFFFFFFFu, isMatch && mIdx >= Pc);
-        if (stopMask) {                                              // mc:2337-2340: "Fatal Error", stop before that token
-            const int first = __ffs(stopMask) - 1;
-            valid = valid && lane < first;
-            isMatch = isMatch && valid;
-            stop = true;
-        }
-        uint32_t l = 0, p = 0;
-        bool badLane = false;
-        if (isMatch) {
-            if (mIdx >= nL) badLane = true;                          // its Golomb code ran past the stream
-            else {
-                l = __ldcg(lv + mIdx);
-                const uint32_t bp = kPBits * mIdx;                   // decombine_bits, mc:1315-1338
-                const uint32_t by = bp >> 3;
-                const uint32_t raw = (uint32_t)__ldcg(pk + by) | ((uint32_t)__ldcg(pk + by + 1) << 8) | ((uint32_t)__ldcg(pk + by + 2) << 16);
-                p = (raw >> (bp & 7)) & 0x7FFu;
-                if (l > (uint32_t)kMaxLen) badLane = true;
-            }
-        }
-        const uint32_t len1 = valid ? l + 1 : 0;
-        uint32_t inc = len1;
+    uint32_t cur = 0, mBase = 0, flushed = 0;                        // cur / flushed live in warp 0
+    bool bad = false;
+    if (tid == 0) sm.fin = 0;
+    for (uint32_t tS = 0; tS < T; tS += DEC_SUPER) {
+        // ---- gather -------------------------------------------------------------------------------------
+        const uint32_t tb = tS + 8u * tid;
+        const uint32_t nvalid = tb < T ? min(8u, T - tb) : 0u;
+        const uint32_t flags = nvalid ? (uint32_t)__ldcg(bm + (tb >> 3)) : 0xFFu;
+        const uint32_t zmask = ~flags & ((1u << nvalid) - 1u);       // match tokens among mine
+        uint32_t inc = (uint32_t)__popc(zmask);
+        const uint32_t mine = inc;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
             if (lane >= d) inc += v;
         }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        const uint32_t pos = cur + inc - len1;
-        if (valid && !badLane && ((l && (p == 0 || p > pos)) || (unsigned long long)pos + l + 1 > kBlockBytes + 8)) badLane = true;
-        if (__any_sync(0xFFFFFFFFu, badLane)) { bad = true; break; }
-        const uint32_t lit = valid ? (uint32_t)__ldcg(cs + t) : 0u;
-        // a token is independent when all its source bytes were produced before this trip
-        const bool dep = isMatch && l && (pos - p + l > cur);
-        if (valid) {
-            if (!dep) for (uint32_t k = 0; k < l; k++) ring[(pos + k) & RM] = ring[(pos - p + k) & RM];   // mc:1730-1732
-            ring[(pos + l) & RM] = (uint8_t)lit;                                                         // mc:1734
-        }
-        __syncwarp();
-        uint32_t depMask = __ballot_sync(0xFFFFFFFFu, dep);
-        while (depMask) {                                            // in order: each may read what the previous wrote
-            const int d = __ffs(depMask) - 1;
-            depMask &= depMask - 1;
-            const uint32_t pd = __shfl_sync(0xFFFFFFFFu, pos, d), ld = __shfl_sync(0xFFFFFFFFu, l, d),
-                           sd = __shfl_sync(0xFFFFFFFFu, p, d);
-            // the source window [pd-sd, pd) is final; an overlapping copy repeats it with period sd
-            for (uint32_t k = lane; k < ld; k += 32) {
-                const uint32_t off = sd >= ld ? k : k % sd;
-                ring[(pd + k) & RM] = ring[(pd - sd + off) & RM];
+        if (lane == 31) sm.warpTot[warp] = inc;
+        __syncthreads();
+        uint32_t rank = mBase + inc - mine, tot = 0;
+#pragma unroll
+        for (int w = 0; w < DEC_THREADS / 32; w++) { const uint32_t v = sm.warpTot[w]; if (w < warp) rank += v; tot += v; }
+        mBase += tot;
+        unsigned long long lits = 0;
+        if (nvalid) lits = __ldcg(reinterpret_cast<const unsigned long long *>(cs + tb));   // 8-byte aligned, buffer is padded
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t L = DEC_TOK_NONE, P = 0;
+            if ((uint32_t)i < nvalid) {
+                L = 0;
+                if ((zmask >> i) & 1u) {
+                    const uint32_t m = rank + (uint32_t)__popc(zmask & ((1u << i) - 1u));
+                    if (m >= Pc) L = DEC_TOK_STOP;                   // mc:2337-2340: "Fatal Error", stop before this token
+                    else if (m >= nL) L = DEC_TOK_BAD;               // its Golomb code ran past the stream
+                    else {
+                        L = __ldcg(lv + m);
+                        const uint32_t bp = kPBits * m, by = bp >> 3;   // decombine_bits, mc:1315-1338
+                        const uint32_t raw = (uint32_t)__ldcg(pk + by) | ((uint32_t)__ldcg(pk + by + 1) << 8) |
+                                             ((uint32_t)__ldcg(pk + by + 2) << 16);
+                        P = (raw >> (bp & 7)) & 0x7FFu;
+                        if (L > (uint32_t)kMaxLen) L = DEC_TOK_BAD;
+                    }
+                }
             }
-            __syncwarp();
+            sm.tokL[8 * tid + i] = (uint16_t)L;
+            sm.tokP[8 * tid + i] = (uint16_t)P;
+            sm.tokC[8 * tid + i] = (uint8_t)(lits >> (8 * i));
         }
-        // ---- flush the finished whole words to HBM ---------------------------------------------------
-        const uint32_t newCur = cur + total;
-        const uint32_t fe = newCur & ~3u;
-        for (uint32_t w = (flushed >> 2) + lane; w < (fe >> 2); w += 32)
-            o32[w] = reinterpret_cast<const uint32_t *>(ring)[w & (RM >> 2)];
-        flushed = fe;
-        cur = newCur;
-        mBase += __popc(mmask);
-        __syncwarp();
+        __syncthreads();
+        // ---- replay ---------------------------------------------------------------------------------------
+        if (warp == 0) {
+            const uint32_t nTok = min((uint32_t)DEC_SUPER, T - tS);
+            bool stop = false;
+            for (uint32_t bb = 0; bb < nTok && !stop && !bad; bb += 32) {
+                uint32_t l = sm.tokL[bb + lane];
+                const uint32_t p = sm.tokP[bb + lane], lit = sm.tokC[bb + lane];
+                bool valid = l != DEC_TOK_NONE;
+                const uint32_t special = __ballot_sync(0xFFFFFFFFu, l == DEC_TOK_STOP || l == DEC_TOK_BAD);
+                if (special) {
+                    const int first = __ffs(special) - 1;
+                    if (__shfl_sync(0xFFFFFFFFu, l, first) == DEC_TOK_BAD) { bad = true; break; }
+                    valid = valid && lane < first;
+                    stop = true;
+                }
+                if (!valid) l = 0;
+                const uint32_t len1 = valid ? l + 1 : 0;
+                uint32_t sc = len1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, sc, d);
+                    if (lane >= d) sc += v;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, sc, 31);
+                const uint32_t pos = cur + sc - len1;
+                const bool badLane = valid && ((l && (p == 0 || p > pos)) || (unsigned long long)pos + l + 1 > kBlockBytes);
+                if (__any_sync(0xFFFFFFFFu, badLane)) { bad = true; break; }
+                // a token is independent when all its source bytes were produced before this trip
+                const bool dep = valid && l && (pos - p + l > cur);
+                if (valid) {
+                    if (!dep) for (uint32_t k = 0; k < l; k++) ring[(pos + k) & RM] = ring[(pos - p + k) & RM];   // mc:1730-1732
+                    ring[(pos + l) & RM] = (uint8_t)lit;                                                         // mc:1734
+                }
+                __syncwarp();
+                uint32_t depMask = __ballot_sync(0xFFFFFFFFu, dep);
+                while (depMask) {                                    // in order: each may read what the previous wrote
+                    const int d = __ffs(depMask) - 1;
+                    depMask &= depMask - 1;
+                    const uint32_t pd = __shfl_sync(0xFFFFFFFFu, pos, d), ld = __shfl_sync(0xFFFFFFFFu, l, d),
+                                   sd = __shfl_sync(0xFFFFFFFFu, p, d);
+                    // the source window [pd-sd, pd) is final; an overlapping copy repeats it with period sd
+                    for (uint32_t k = lane; k < ld; k += 32) {
+                        const uint32_t off = sd >= ld ? k : k % sd;
+                        ring[(pd + k) & RM] = ring[(pd - sd + off) & RM];
+                    }
+                    __syncwarp();
+                }
+                // ---- flush the finished whole words to HBM ---------------------------------------------
+                const uint32_t newCur = cur + total;
+                const uint32_t fe = newCur & ~3u;
+                for (uint32_t w = (flushed >> 2) + lane; w < (fe >> 2); w += 32)
+                    o32[w] = reinterpret_cast<const uint32_t *>(ring)[w & (RM >> 2)];
+                flushed = fe;
+                cur = newCur;
+                __syncwarp();
+            }
+            if (lane == 0 && (stop || bad)) sm.fin = 1;
+        }
+        __syncthreads();
+        if (sm.fin) break;
     }
-    if (!bad) for (uint32_t i = flushed + lane; i < cur; i += 32) o[i] = ring[i & RM];
-    if (lane == 0) outLen[b] = bad ? DEC_BAD : cur;
+    if (warp == 0) {
+        if (!bad) for (uint32_t i = flushed + lane; i < cur; i += 32) o[i] = ring[i & RM];
+        if (lane == 0) outLen[b] = bad ? DEC_BAD : cur;
+    }
 }
 
 int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out,
@@ -392,7 +457,7 @@ int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlo
 {
     // the reference decodes into zero-initialised buffers (mc:2270,2282,2291,2305)
     cudaMemsetAsync(d_scratch, 0, scratchPerBlock * nBlocks, st);
-    k_decode<<<nBlocks, 128, 0, st>>>(d_file, d_recOff, d_out, d_outLen, d_scratch, scratchPerBlock);
+    k_decode<<<nBlocks, DEC_THREADS, 0, st>>>(d_file, d_recOff, d_out, d_outLen, d_scratch, scratchPerBlock);
     return 1;
 }
 
