@@ -223,6 +223,55 @@ def test_round_trip_container():
         assert api.decompress(blob) == data.tobytes()
 
 
+def test_round_trip_hard_streams_for_the_decoder():
+    """Long Huffman codes (tree walk beyond the 11-bit table), Golomb runs of 64 ones (l = 257), periodic
+    overlapping copies, a ragged last block: the speculative decoder must land on the sequential result,
+    i.e. on what the reference's decoder makes of the same container."""
+    rng = np.random.default_rng(4242)
+    geo = np.minimum(rng.geometric(0.45, size=(1 << 20) + 4097) - 1, 255).astype(np.uint8)     # codes up to ~20 bits
+    cases = [("geometric", geo),
+             ("byterun", datagen.gen("byterun", (2 << 20) + 33, seed=8)),
+             ("periodic", datagen.gen("periodic", (1 << 20) + 1, seed=8)),
+             ("randm", datagen.gen("randm", 1 << 20, seed=8)),
+             ("two_symbols", (rng.integers(0, 2, size=300001, dtype=np.uint8) * 7 + 65).astype(np.uint8)),
+             ("mixed", datagen.gen("mixed", (5 << 20) + 12345, seed=8))]
+    o = oracle()
+    for name, data in cases:
+        blob = api.compress(data)
+        want = o.decompress_file(blob, len(data) + 64)       # the reference's decoder (lossy on single-symbol streams, App. B1)
+        got = api.decompress(blob)
+        assert got == want, "%s: differs at byte %d of %d/%d" % (name, _first_diff(got, want), len(got), len(want))
+        if name in ("geometric", "randm", "mixed"):          # no single-symbol stream in these: the round trip is exact
+            assert got == data.tobytes(), name
+
+
+def _section_end(p, at):
+    tn = p[at]
+    w_at = at + 1 + (2 * tn + 7) // 8 + 2 * tn
+    return w_at + 4 + 4 * int.from_bytes(p[w_at:w_at + 4], "little")
+
+
+def test_decoder_stops_where_the_reference_does_when_matches_run_out():
+    """mc:2337-2340: a match flag with no distance left prints "Fatal Error" and ends the block early.
+    Payloads with the stored match count lowered must decode to the same prefix as the reference."""
+    o = oracle()
+    for name, buf in small_buffers(seed=77, count=16, max_len=6000):
+        if len(buf) < 64:
+            continue
+        p = bytearray(o.compress_block(buf))
+        T = int.from_bytes(p[0:4], "little")
+        if (T + 7) // 8 <= 1:
+            continue
+        at = _section_end(p, _section_end(p, 4))            # past the bitmap and c sections: the Pc field
+        pc = int.from_bytes(p[at:at + 4], "little")
+        for new_pc in {0, pc // 2, max(0, pc - 1)} - {pc}:
+            q = bytearray(p)
+            q[at:at + 4] = new_pc.to_bytes(4, "little")
+            want = o.decompress_block(bytes(q))
+            got = api.my_decompress_file_lz77(bytes(q))
+            assert got == want, (name, pc, new_pc, len(got), len(want))
+
+
 def test_multi_gpu_block_sharding_matches_single_gpu():
     """fcx_compress_lz77 with a multi-device mask shards contiguous block ranges over the GPUs;
     the container must not depend on the device count."""
