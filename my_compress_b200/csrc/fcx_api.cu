@@ -243,6 +243,8 @@ struct BatchHooks {
     cudaEvent_t *waitBefore = nullptr;
     cudaEvent_t *recordAfter = nullptr;
     uint64_t *hostCursor = nullptr;
+    const uint32_t *sizes = nullptr;        // blocks per batch (uneven pipeline plan); null = the context's uniform step
+    uint32_t nSizes = 0;
 };
 
 static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out, uint64_t outCap, uint32_t flags,
@@ -273,8 +275,10 @@ static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_o
     }
     const uint32_t step = c->batchBlocks ? std::min(c->batchBlocks, c->maxBlocks) : c->maxBlocks;
     uint32_t batch = 0;
-    for (uint64_t first = 0; first < nBlocks; first += step, batch++) {
-        const uint32_t nb = (uint32_t)std::min<uint64_t>(step, nBlocks - first);
+    for (uint64_t first = 0, adv = 0; first < nBlocks; first += adv, batch++) {
+        const uint32_t want = (hooks && hooks->sizes && batch < hooks->nSizes) ? hooks->sizes[batch] : step;
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(std::min(want, c->maxBlocks), nBlocks - first);
+        adv = nb;
         if (hooks && hooks->waitBefore) CK(cudaStreamWaitEvent(st, hooks->waitBefore[batch], 0));
         const uint8_t *bin = d_in + first * kBlockBytes;
         const uint64_t rem = n - first * kBlockBytes;
@@ -431,16 +435,34 @@ extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, ui
         int rc = slot_prepare(s, devs[g], len, bound);
         if (rc) { rcs[g] = rc; errs[g] = g_err; return; }
         const uint64_t blocks = (len + kBlockBytes - 1) / kBlockBytes;
-        // sub-batch size: >= 16 blocks keeps the GPU busy, <= 8 batches keeps per-batch latency small
+        // Pipeline plan.  Only the first batch's upload and the last batch's download are exposed, so both
+        // are small; H2D runs ~3x faster than the kernels, so the second batch can already be five times the
+        // first, and the rest goes in a few large batches (every batch pays ~0.15 ms of latency-bound kernels).
 #ifndef FCX_PIPE_MIN_BLOCKS
 #define FCX_PIPE_MIN_BLOCKS 16
 #endif
-#ifndef FCX_PIPE_MAX_BATCHES
-#define FCX_PIPE_MAX_BATCHES 8
-#endif
-        uint32_t sb = (uint32_t)std::max<uint64_t>(FCX_PIPE_MIN_BLOCKS, (blocks + FCX_PIPE_MAX_BATCHES - 1) / FCX_PIPE_MAX_BATCHES);
-        sb = std::min<uint32_t>(sb, s.ctxBlocks);
-        const uint32_t nBatches = blocks ? (uint32_t)((blocks + sb - 1) / sb) : 0;
+        std::vector<uint32_t> plan;
+        if (blocks > FCX_PIPE_MIN_BLOCKS) {
+            const uint32_t B = (uint32_t)blocks, cap = s.ctxBlocks;
+            const uint32_t edge = std::min<uint32_t>(16, std::max<uint32_t>(2, B / 16));
+            uint32_t rem = B - 2 * edge;
+            plan.push_back(edge);
+            const uint32_t second = std::min<uint32_t>(rem, 4 * edge + 4);
+            if (second) plan.push_back(second);
+            rem -= second;
+            // large inputs taper at the end as well: the download of a big batch would otherwise outlast the
+            // small last batch it is meant to hide behind (incompressible data downloads as much as it uploads)
+            const uint32_t taper = (B >= 256 && rem > second) ? second : 0;
+            rem -= taper;
+            if (rem) {
+                const uint32_t lim = std::min<uint32_t>(cap, B >= 256 ? 128u : cap);
+                const uint32_t k = std::max<uint32_t>(std::min<uint32_t>(5, std::max<uint32_t>(1, rem / 32)), (rem + lim - 1) / lim);
+                for (uint32_t i = 0; i < k; i++) plan.push_back(rem * (i + 1) / k - rem * i / k);
+            }
+            if (taper) plan.push_back(taper);
+            plan.push_back(edge);
+        }
+        const uint32_t nBatches = (uint32_t)plan.size();
         if (nBatches < 2 || nBatches > kMaxPipeBatches) {                    // small input: nothing to overlap
             s.ctx->batchBlocks = 0;
             if (len && cudaMemcpyAsync(s.dIn, in + off, len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
@@ -458,15 +480,18 @@ extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, ui
             return;
         }
         cudaError_t e = cudaSuccess;
+        uint64_t o = 0;
         for (uint32_t k = 0; k < nBatches && e == cudaSuccess; k++) {
-            const uint64_t o = (uint64_t)k * sb * kBlockBytes, l = std::min<uint64_t>((uint64_t)sb * kBlockBytes, len - o);
+            const uint64_t l = std::min<uint64_t>((uint64_t)plan[k] * kBlockBytes, len - o);
             e = cudaMemcpyAsync(s.dIn + o, in + off + o, l, cudaMemcpyHostToDevice, s.h2d);
             if (e == cudaSuccess) e = cudaEventRecord(s.evIn[k], s.h2d);
+            o += l;
         }
         if (e != cudaSuccess) { rcs[g] = fail(FCX_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); errs[g] = g_err; return; }
         BatchHooks hooks;
         hooks.waitBefore = s.evIn.data(); hooks.recordAfter = s.evOut.data(); hooks.hostCursor = s.hostCursor;
-        s.ctx->batchBlocks = sb;
+        hooks.sizes = plan.data(); hooks.nSizes = nBatches;
+        s.ctx->batchBlocks = 0;
         if (((uintptr_t)s.dIn & 15) || ((uintptr_t)s.dOut & 15)) rc = fail(FCX_ERR_ARG, "device pointers must be 16-byte aligned");
         if (rc == FCX_OK) rc = run_batches(s.ctx, s.dIn, len, s.dOut, bound, g == 0 ? FCX_WITH_HEADER : 0, n, (uint32_t)nBlocks, &hooks);
         s.ctx->batchBlocks = 0;
