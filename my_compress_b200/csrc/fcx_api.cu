@@ -153,6 +153,8 @@ extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks
     A(dalloc(c, &w.chunkBits, (size_t)w.maxChunks));
     A(dalloc(c, &w.chunkBitOff, (size_t)w.maxChunks));
     A(dalloc(c, &w.chunkDesc, (size_t)w.maxChunks));
+    A(dalloc(c, &w.segCost, B * 4 + 1));
+    A(dalloc(c, &w.encSplit, (size_t)kMaxEncCtas + 1));
     A(dalloc(c, &w.blkOff, B + 1));
     A(dalloc(c, &w.totals, (size_t)TOT_WORDS));
     A(dalloc(c, &w.counters, (size_t)C_WORDS));

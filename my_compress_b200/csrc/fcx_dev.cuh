@@ -35,6 +35,7 @@ constexpr int kParseEntries = 258;                                // a chain ent
 constexpr int kChunkSyms = 8192;                  // symbols per encode/histogram chunk
 constexpr int kMaxChunksPerBlock = 128 + 17 + 45 + 14;   // c, bitmap, p, golomb (ceil + 1)
 constexpr int kSegHdrStride = 576;                // 1 + 64 + 510 rounded up
+constexpr int kMaxEncCtas = 4096;                 // upper bound of the k_encode_w grid
 
 // per-block meta words
 enum { M_T = 0, M_PC, M_G, M_GBITS, M_S0, M_S1, M_S2, M_S3, M_WORDS };
@@ -71,6 +72,8 @@ struct Ws {
     uint32_t *chunkBits;  // [maxChunks]
     uint32_t *chunkBitOff;// [maxChunks] bit offset inside the segment's code words
     uint4 *chunkDesc;     // [maxChunks] everything k_encode needs for one chunk (see CD_* in fcx_huff.cu)
+    uint32_t *segCost;    // [4*maxBlocks+1] estimated encode cost per stream, then its exclusive prefix sum
+    uint32_t *encSplit;   // [kMaxEncCtas+1] first chunk of every k_encode_w CTA (cost-balanced contiguous ranges)
     uint64_t *blkOff;     // [maxBlocks+1] byte offset (in d_out) of each "u32 size|payload" record
     uint32_t *totals;     // [TOT_WORDS]
     uint64_t *counters;   // [C_WORDS]
