@@ -51,7 +51,7 @@ def env_int(name, default):
 
 
 def encode_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of k_encode per launch, from the committed ncu
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_encode_w per launch, from the committed ncu
     --set full capture of this workload (profiles/encode_traffic.json); None if there is none."""
     path = os.path.join(ROOT, "profiles", "encode_traffic.json")
     try:
@@ -282,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = stats["s_in"] + stats["s_out"]
     achieved = alg_bytes / (enc_ms * 1e-3) / 1e9 if enc_ms > 0 else 0.0
     stage_total = sum(stage.values())
-    roofline = {"kernel": "k_encode", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_encode_w", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": encode_traffic(args.workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": enc_ms,
                 "share_of_step": enc_ms / stage_total if stage_total else None}
