@@ -42,6 +42,15 @@ struct JumpSmem {
 __device__ __forceinline__ int jphys(int i) { return i + 2 * (i >> 4); }
 __device__ __forceinline__ int code_len(uint32_t code) { return code ? (int)code + 2 : 0; }
 
+// All-literal tiles (incompressible input: ~60 % of the tiles of random data) need no jump tables: every
+// position from the entry on is a one-byte token, so the exit offset is 0, the counts are (limit - entry, 0, 0)
+// and the emit is a byte copy plus a run of set flag bits.  CTA-uniform test on the tile's len codes.
+__device__ __forceinline__ bool tile_has_match(const uint8_t *lcG, int tb)
+{
+    const uint4 v = reinterpret_cast<const uint4 *>(lcG + tb)[threadIdx.x];
+    return __syncthreads_or((v.x | v.y | v.z | v.w) != 0u) != 0;
+}
+
 // stage the tile's len codes and build J1 / J2 (ends with a __syncthreads)
 __device__ __forceinline__ void build_jumps(JumpSmem &sm, const uint8_t *lcG, int tb, int limit)
 {
@@ -108,8 +117,12 @@ k_parse_exits(const uint32_t *__restrict__ blkLen, const uint8_t *__restrict__ l
     const int n = (int)blkLen[b];
     const int tb = tile * PT;
     if (tb >= n) return;
-    build_jumps(sm, lenCode + (size_t)b * kBlockBytes, tb, min(PT, n - tb));
     uint16_t *ex = ws.parseExit + ((size_t)b * kParseTilesPerBlock + tile) * PT_ENTRIES;
+    if (!tile_has_match(lenCode + (size_t)b * kBlockBytes, tb)) {     // codes past n are never non-zero (k_match writes none)
+        for (int e0 = tid; e0 < PT_ENTRIES; e0 += PT_THREADS) ex[e0] = 0;
+        return;
+    }
+    build_jumps(sm, lenCode + (size_t)b * kBlockBytes, tb, min(PT, n - tb));
     for (int e0 = tid; e0 < PT_ENTRIES; e0 += PT_THREADS) {
         int e = e0;
         while (e < PT) e = sm.J2[jphys(e)];            // <= 16 hops, one mid-tile each
@@ -168,6 +181,13 @@ k_parse_count(const uint32_t *__restrict__ blkLen, const uint8_t *__restrict__ l
     const int tb = tile * PT;
     if (tb >= n) return;
     const int limit = min(PT, n - tb);
+    if (!tile_has_match(lenCode + (size_t)b * kBlockBytes, tb)) {
+        if (tid == 0) {
+            const int entry = ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile];
+            ws.tileCnt[(size_t)b * kParseTilesPerBlock + tile] = make_uint4((uint32_t)max(limit - entry, 0), 0, 0, 0);
+        }
+        return;
+    }
     build_jumps(sm, lenCode + (size_t)b * kBlockBytes, tb, limit);
     resolve_entries(sm, ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile]);
     uint32_t tok, mat, gb;
@@ -270,6 +290,37 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     const int limit = min(PT, n - tb);
     const uint8_t *x = in + (size_t)b * kBlockBytes;
     const uint16_t *dsG = dist + (size_t)b * kBlockBytes;
+    if (!tile_has_match(lenCode + (size_t)b * kBlockBytes, tb)) {
+        // every token is a literal: c = the bytes themselves, flags = a run of ones at the tile's token rank
+        const int entry = ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile];
+        const uint32_t tileTok = (uint32_t)max(limit - entry, 0);
+        const uint4 bases = ws.tileCnt[(size_t)b * kParseTilesPerBlock + tile];
+        const uint8_t *src = x + tb + entry;
+        uint8_t *cOut = ws.strm[1] + (size_t)b * ws.strmStride[1] + bases.x;
+        // byte copy between two unaligned ranges: 4-byte stores on the destination's alignment, bytes at the edges
+        const uint32_t head = min(tileTok, (uint32_t)((4u - ((uint32_t)(size_t)cOut & 3u)) & 3u));
+        if ((uint32_t)tid < head) cOut[tid] = src[tid];
+        const uint32_t nW = (tileTok - head) >> 2;
+        for (uint32_t k = tid; k < nW; k += PT_THREADS) {
+            const uint8_t *q = src + head + 4 * k;
+            reinterpret_cast<uint32_t *>(cOut + head)[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        }
+        const uint32_t done = head + 4 * nW;
+        if ((uint32_t)tid < tileTok - done) cOut[done + tid] = src[done + tid];
+        // flag bits [bases.x, bases.x + tileTok) of the (pre-zeroed) bitmap stream
+        if (tileTok) {
+            uint32_t *fs = reinterpret_cast<uint32_t *>(ws.strm[0] + (size_t)b * ws.strmStride[0]);
+            const uint32_t b0 = bases.x, b1 = bases.x + tileTok;            // bit range
+            const uint32_t w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
+            for (uint32_t w = w0 + tid; w <= w1; w += PT_THREADS) {
+                uint32_t m = 0xFFFFFFFFu;
+                if (w == w0) m &= 0xFFFFFFFFu << (b0 & 31);
+                if (w == w1 && (b1 & 31)) m &= 0xFFFFFFFFu >> (32 - (b1 & 31));
+                if (m == 0xFFFFFFFFu) fs[w] = m; else atomicOr(&fs[w], m);   // edge words are shared with the neighbouring tiles
+            }
+        }
+        return;
+    }
     // stage bytes (+ look-ahead for c = x[i+len]) and zero the bit buffers; distances are read
     // straight from global memory, only for the tokens that are matches
     for (int v = tid; v < (PT + PT_LOOK) / 16; v += PT_THREADS) {
