@@ -50,7 +50,24 @@ def build(force=False, verbose=False):
     return LIB
 
 
+# Test-only variant: a 96-word stage per warp, so that ordinary 8-bit streams overflow it and k_encode_w's
+# direct (atomicOr from registers) path for over-dense sub-chunks is exercised by tests/test_gpu_parity.py.
+LIB_SMALLSTAGE = os.path.join(HERE, "libfcx_smallw.so")
+
+
+def build_test_variants(force=False):
+    if not force and os.path.exists(LIB_SMALLSTAGE) and os.path.getmtime(LIB_SMALLSTAGE) >= os.path.getmtime(LIB):
+        return LIB_SMALLSTAGE
+    cmd = [NVCC] + FLAGS + ["-DFCX_ENCW_STAGE_WORDS=96"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_SMALLSTAGE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libfcx_smallw.so")
+    return LIB_SMALLSTAGE
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
     build_cli(force=True)
+    build_test_variants(force=True)
     print(LIB)

@@ -853,6 +853,16 @@ constexpr uint32_t EW_STAGE_BITS = (uint32_t)EW_STAGE_WORDS * 32u - 32u;
 constexpr uint32_t EW_PREF_SHIFT = 18;                 // low 18 bits: bit count of one sub-chunk
 static_assert((uint32_t)kChunkSyms * 24u < (1u << EW_PREF_SHIFT), "a chunk's bit count fits the prefix field");
 
+// Stage swizzle of k_encode_w (same permutation as k_encode's).  Off by default: the streams whose runs all
+// have the same length -- the case the swizzle exists for -- are the fixed 8-bit ones, and those no longer
+// touch the stage; without it every flush is three instructions shorter.
+#ifndef FCX_ENCW_SWIZZLE
+#define FCX_ENCW_SWIZZLE 0
+#endif
+__device__ __forceinline__ uint32_t ew_swz_byte(uint32_t byteOff) { return FCX_ENCW_SWIZZLE ? enc_swz_byte(byteOff) : byteOff; }
+__device__ __forceinline__ uint32_t ew_swz_word(uint32_t k) { return FCX_ENCW_SWIZZLE ? enc_swz_word(k) : k; }
+__device__ __forceinline__ uint32_t ew_swz_unit(uint32_t v) { return FCX_ENCW_SWIZZLE ? enc_swz_unit(v) : v; }
+
 struct EncWSmem {
     alignas(1024) uint32_t stage[EW_WARPS][EW_STAGE_WORDS];
     alignas(16) unsigned long long tab[256 * 16];      // tab[sym*16 + (lane & 15)] = code | (u64)(1 << len) << 32
@@ -1046,7 +1056,7 @@ __device__ __forceinline__ uint32_t encw_sub(uint32_t *__restrict__ out32, uint3
             lo |= bitsq << accBits;
             const uint32_t hi = __funnelshift_l(bitsq, 0u, accBits);     // bits that spill past bit 31 (0 when accBits == 0)
             accBits += lenq;
-            if (accBits >= 32) { enc_sts(stageA + enc_swz_byte(w), lo); w += 4; lo = hi; }
+            if (accBits >= 32) { enc_sts(stageA + ew_swz_byte(w), lo); w += 4; lo = hi; }
             accBits &= 31;
         }
         tail = lo; tailIdx = w >> 2;
@@ -1054,9 +1064,9 @@ __device__ __forceinline__ uint32_t encw_sub(uint32_t *__restrict__ out32, uint3
     // the tail of run t-1 lives in the low bits of the head word of run t
     const uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
     if (active) {
-        const uint32_t headA = stageA + 4 * enc_swz_word(p0 >> 5);
+        const uint32_t headA = stageA + 4 * ew_swz_word(p0 >> 5);
         if (lane > 0) enc_sts(headA, enc_lds(headA) | prevTail);                          // own word, own earlier store
-        if ((uint32_t)lane == nAct - 1) enc_sts(stageA + 4 * enc_swz_word(tailIdx), tail);   // nobody follows: park the tail
+        if ((uint32_t)lane == nAct - 1) enc_sts(stageA + 4 * ew_swz_word(tailIdx), tail);   // nobody follows: park the tail
     }
     __syncwarp();
     // ---- copy out: whole 16-byte units as 128-bit stores, the two shared edge words by atomicOr ----
@@ -1066,24 +1076,24 @@ __device__ __forceinline__ uint32_t encw_sub(uint32_t *__restrict__ out32, uint3
     if (vBeg < vEnd) {
         for (uint32_t v = vBeg + lane; v < vEnd; v += 32) {
             uint4 q;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stageA + 16 * enc_swz_unit(v)));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stageA + 16 * ew_swz_unit(v)));
             reinterpret_cast<uint4 *>(dst)[v] = q;
         }
         if (lane < 8) {                                              // scalar edges
             const uint32_t k = lane < 4 ? first + lane : 4 * vEnd + (lane - 4);
             const bool inHead = lane < 4 && k < 4 * vBeg, inTail = lane >= 4 && k < last;
             if (inHead || inTail) {
-                const uint32_t v = enc_lds(stageA + 4 * enc_swz_word(k));
+                const uint32_t v = enc_lds(stageA + 4 * ew_swz_word(k));
                 if (k == first && fbit) atomicOr(&dst[k], v); else dst[k] = v;
             }
         }
     } else {
         for (uint32_t k = first + lane; k < last; k += 32) {
-            const uint32_t v = enc_lds(stageA + 4 * enc_swz_word(k));
+            const uint32_t v = enc_lds(stageA + 4 * ew_swz_word(k));
             if (k == first && fbit) atomicOr(&dst[k], v); else dst[k] = v;
         }
     }
-    if (lane == 0 && rem) atomicOr(&dst[last], enc_lds(stageA + 4 * enc_swz_word(last)));
+    if (lane == 0 && rem) atomicOr(&dst[last], enc_lds(stageA + 4 * ew_swz_word(last)));
     __syncwarp();                                       // the stage is rewritten by the next sub-chunk
     return through;
 }

@@ -47,10 +47,11 @@ constexpr int MT_NSUB = MT_REGION / MT_SUB;      // 6
 #endif
 constexpr int MT_HBITS = FCX_MT_HBITS;
 constexpr int MT_HB = 1 << MT_HBITS;             // buckets per sub-region
-constexpr int MT_LOOK = 272;                     // >= 257 + 8
+constexpr int MT_LOOK = 272;                     // >= 257 + 8 + 7: the 8-byte visit window, then lcp_capped's look-ahead
 constexpr int MT_THREADS = 256;
 constexpr int MT_PER_THREAD = MT_TILE / MT_THREADS;   // 16
 constexpr int MT_PROBES = 64;                         // positions sampled per tile
+constexpr int MT_PROBE_CAP = 40;                      // probed matches are not followed beyond this
 constexpr int MT_LONG_MEAN = 12;                      // mean probed match length that switches a tile to lazy evaluation
 constexpr int MT_SPEC_STRIDE = FCX_MT_SPEC_STRIDE;                    // lazy mode: a speculative chain starts every 32 positions
 constexpr uint32_t MT_NONE = 0xFFFF;
@@ -101,16 +102,28 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(uint32_t a)
     return __funnelshift_r(lds_u32(al), lds_u32(al + 4), (a & 3u) * 8);
 }
 
+// length of the common prefix of x[a..] and x[b..], at most cap.  Both streams are read as ALIGNED words with
+// the previous word carried in a register (one load + one funnel shift per stream per 4 bytes, two steps per
+// trip); reads up to 11 bytes past the last compared byte, inside the look-ahead padding of xs.
 __device__ __forceinline__ int lcp_capped(uint32_t xsA, int a, int b, int cap)
 {
+    const uint32_t pa = xsA + (uint32_t)a, pb = xsA + (uint32_t)b;
+    uint32_t aa = pa & ~3u, ab = pb & ~3u;
+    const uint32_t sa = (pa & 3u) * 8, sb = (pb & 3u) * 8;
+    uint32_t wa0 = lds_u32(aa), wb0 = lds_u32(ab);
     int k = 0;
     while (k < cap) {
-        const uint32_t d = lds_u32_unaligned(xsA + a + k) ^ lds_u32_unaligned(xsA + b + k);
-        if (d) {
-            const int m = k + ((__ffs(d) - 1) >> 3);
+        const uint32_t wa1 = lds_u32(aa + 4), wb1 = lds_u32(ab + 4);
+        const uint32_t wa2 = lds_u32(aa + 8), wb2 = lds_u32(ab + 8);
+        const uint32_t d0 = __funnelshift_r(wa0, wa1, sa) ^ __funnelshift_r(wb0, wb1, sb);
+        const uint32_t d1 = __funnelshift_r(wa1, wa2, sa) ^ __funnelshift_r(wb1, wb2, sb);
+        if (d0 | d1) {
+            const int m = k + (d0 ? ((__ffs(d0) - 1) >> 3) : 4 + ((__ffs(d1) - 1) >> 3));
             return m < cap ? m : cap;
         }
-        k += 4;
+        wa0 = wa2; wb0 = wb2;
+        aa += 8; ab += 8;
+        k += 8;
     }
     return cap;
 }
@@ -380,8 +393,10 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const int i = regionBase + si;
             const int cap = min(kMaxLen, n - 1 - i);
             if (i > 0 && cap >= kMinLen) {
+                // the probe only has to tell "mean length >= 12" from "short": matches are followed to 40 bytes at
+                // most (one probe lane walking a 257-byte match kept the other 192 threads at the barrier)
                 int bl = 0, bs = 0;
-                match_one(ctx, si, cap, bl, bs);
+                match_one(ctx, si, min(cap, MT_PROBE_CAP), bl, bs);
                 L = bl >= kMinLen ? bl : 0;
             }
         }

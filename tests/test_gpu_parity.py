@@ -149,6 +149,42 @@ def test_huffman_encode_groups_and_chunk_edges(dc):
             assert got == want, "m=%d n=%d: section differs at byte %d of %d/%d" % (m, n, _first_diff(got, want), len(got), len(want))
 
 
+def test_huffman_encode_fixed_8bit_streams(dc):
+    """A flat histogram over all 256 bytes gives every symbol an 8-bit code; k_encode_w then translates
+    bytes instead of packing bits (EW_FIXED8).  Sizes sit around its units: 4 symbols per word, 1024 per
+    warp, 8192 per chunk, and the ragged 1..3 bytes of a stream end; the section's byte offset inside the
+    probe container varies with the header size, so all four word alignments occur across the cases."""
+    o = oracle()
+    rng = np.random.default_rng(123)
+    for n in (1024, 1025, 1026, 1027, 2047, 2048, 4099, 8191, 8192, 8193, 8192 + 1023, 8192 + 1025, 3 * 8192 + 2, 65536 + 7):
+        reps = (n + 255) // 256
+        s = np.concatenate([rng.permutation(256) for _ in range(reps)]).astype(np.uint8)[:n]
+        want = o.huffman_section(s)
+        got = dc.probe_huffman_section(_dev(s))
+        assert got == want, "n=%d: section differs at byte %d of %d/%d" % (n, _first_diff(got, want), len(got), len(want))
+    # as the c stream of a block, where the section starts at whatever byte the bitmap section ends on
+    for n in (70001, 70002, 70003, 70004):
+        x = datagen.uniform_block(n, 31, 0)
+        assert api.my_compress_file_lz77(x) == o.compress_block(x), n
+
+
+def test_encode_direct_path_for_dense_subchunks():
+    """The small-stage build (my_compress_b200/build.py build_test_variants: 96 stage words per warp) sends
+    every sub-chunk denser than ~3 bits per symbol down k_encode_w's direct path; the library is chosen at
+    import time, so the check runs in its own process."""
+    import subprocess
+    import sys
+
+    from my_compress_b200 import build as b
+
+    if not os.path.exists(b.LIB_SMALLSTAGE):
+        pytest.skip("libfcx_smallw.so not built (run __graft_entry__.build())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FCX_LIBFCX=b.LIB_SMALLSTAGE)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_variant.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_block_payloads_vs_oracle_and_golden():
     o = oracle()
     for name, buf in small_buffers(seed=2024):
