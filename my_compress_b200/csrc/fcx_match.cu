@@ -12,8 +12,10 @@
 // (hash of the 3-byte gram) with __match_any_sync, walking its chunks from the top so that
 // head[] ends up holding the lowest slot and up[] the next higher slot of the same hash;
 // head[] also carries the bucket population.
-// A position then walks the chains of the (at most three) sub-regions overlapping its
-// window from the far end towards itself: strict '>' on the length gives the reference's
+// The six chains of a bucket are then linked into one ascending chain over the whole region
+// (the tail of a sub-region's chain points at the head of the next non-empty one, an empty
+// head falls through), so a position walks ONE chain from the first sub-region overlapping
+// its window towards itself: strict '>' on the length gives the reference's
 // farthest-wins tie rule, a candidate is only extended when the byte at the current best
 // length matches, and a hit of the cap ends the walk (nothing nearer can beat it).
 //
@@ -68,12 +70,9 @@ struct MatchSmem {
     uint32_t binStart[MT_BINS];
     uint32_t maxPop;
     uint32_t probeSum;
+    uint16_t tail4[MT_HB];                       // chain tails of sub-region 4 while the chains are linked (0..3: order[])
 };
-
-// byte masks: entry m covers bytes 0..m of an 8-byte little-endian window (m >= 7: all eight)
-__constant__ unsigned long long c_byteMask[9] = {
-    0xFFull, 0xFFFFull, 0xFFFFFFull, 0xFFFFFFFFull, 0xFFFFFFFFFFull, 0xFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFull,
-    0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull};
+static_assert(MT_NSUB == 6 && MT_TILE == 4 * MT_HB, "chain tails of sub-regions 0..3 fit order[], sub-region 4 has tail4[], 5 needs none");
 
 // ---- explicit shared-memory loads (32-bit shared addresses held in registers) -------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,21 +141,13 @@ __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, in
     const uint32_t wsi0 = lds_u32_unaligned(xi), wsi1 = lds_u32_unaligned(xi + 4);
     const uint32_t h = hash24(wsi0, MT_HBITS);
     const int lo = max(si - kWindow, c.minSlot);
-    const int srLast = si >> 10;
     const int sr0 = lo >> 10;
     uint32_t mLo = 0x00FFFFFFu, mHi = 0u;               // bytes 0..bestL must agree to beat bestL
-    // heads of the (at most three) chains to walk, loaded up front; -1 = no further chain
-    const uint32_t hp = c.headB + 2 * (sr0 * MT_HB + h);
-    int s = (int)lds_u16(hp);
-    int next1 = sr0 + 1 <= srLast ? (int)lds_u16(hp + 2 * MT_HB) : -1;
-    int next2 = sr0 + 2 <= srLast ? (int)lds_u16(hp + 4 * MT_HB) : -1;
+    // one ascending chain per bucket over the whole region: enter it at the first sub-region the window touches
+    int s = (int)lds_u16(c.headB + 2 * (sr0 * MT_HB + h));
     while (s < lo) s = (int)lds_u16(upB + 2 * s);       // entries before the window (MT_NONE = 0xFFFF ends it)
     for (;;) {
-        if (s >= si) {                                  // chain exhausted (MT_NONE >= si as well)
-            if (next1 < 0) break;
-            s = next1; next1 = next2; next2 = -1;
-            continue;
-        }
+        if (s >= si) break;                             // chain exhausted (MT_NONE >= si as well)
         const int cur = s;
         s = (int)lds_u16(upB + 2 * cur);
         const uint32_t a = xsB + cur, al = a & ~3u, sh = (a & 3u) * 8;
@@ -175,7 +166,8 @@ __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, in
         if (m > bestL) {
             bestL = m; bestS = cur;
             if (m == cap) break;                        // nothing nearer can beat the cap
-            const unsigned long long mk = c_byteMask[min(m, 8)];   // now bytes 0..m must agree
+            const int nb = min(m, 7) + 1;               // now bytes 0..m must agree (all eight from m = 7 on)
+            const unsigned long long mk = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
             mLo = (uint32_t)mk; mHi = (uint32_t)(mk >> 32);
         }
     }
@@ -343,6 +335,7 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         const int sr = warp;
         uint16_t *head = sm.head + sr * MT_HB;
         uint8_t *pop = sm.pop + sr * (MT_HB / 2);
+        uint16_t *tail = sr < 4 ? sm.order + sr * MT_HB : sm.tail4;   // highest slot of every bucket of this sub-region (not kept for the last one)
         uint32_t myMax = 0;
         for (int ch = MT_SUB / 32 - 1; ch >= 0; ch--) {
             const int slot = sr * MT_SUB + ch * 32 + lane;
@@ -357,6 +350,7 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             __syncwarp();
             if (valid) {
                 sm.up[slot] = higher ? (uint16_t)(sr * MT_SUB + ch * 32 + (__ffs(higher) - 1)) : (uint16_t)old;
+                if (!higher && old == MT_NONE && sr < MT_NSUB - 1) tail[h] = (uint16_t)slot;   // chunks come from the top: the bucket's first entry is its tail
                 if ((grp & ((1u << lane) - 1u)) == 0) {
                     const uint32_t np = min(255u, oldPop + (uint32_t)__popc(grp));
                     head[h] = (uint16_t)slot;
@@ -369,6 +363,20 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) myMax = max(myMax, __shfl_xor_sync(0xFFFFFFFFu, myMax, d));
         if (lane == 0) atomicMax(&sm.maxPop, myMax);
+    }
+    __syncthreads();
+    // ---- link the six chains of every bucket into one; an empty (sub-region, bucket) head falls through ----
+    for (int h = tid; h < MT_HB; h += MT_THREADS) {
+        uint32_t nextHead = sm.head[(MT_NSUB - 1) * MT_HB + h];
+        for (int sr = MT_NSUB - 2; sr >= 0; sr--) {
+            const uint32_t hd = sm.head[sr * MT_HB + h];
+            if (hd != MT_NONE) {
+                const uint32_t t = sr < 4 ? sm.order[sr * MT_HB + h] : sm.tail4[h];
+                sm.up[t] = (uint16_t)nextHead;
+                nextHead = hd;
+            } else
+                sm.head[sr * MT_HB + h] = (uint16_t)nextHead;
+        }
     }
     __syncthreads();
 
