@@ -155,21 +155,28 @@ __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, in
         const uint32_t d0 = __funnelshift_r(w0, w1, sh) ^ wsi0;
         const uint32_t d1 = __funnelshift_r(w1, w2, sh) ^ wsi1;
         if ((d0 & mLo) | (d1 & mHi)) continue;          // cannot beat the current best
-        // strict improvement (or, once bestL >= 7, a candidate agreeing on all eight bytes)
+        // The candidate agrees on bytes 0..bestL (all eight once bestL >= 7): below eight bytes that IS a strict
+        // improvement, no comparison needed (bestL < cap here, or the walk would have ended at the cap).
         const uint32_t dx = d0 ? d0 : d1;               // word holding the first differing byte
-        int m = dx ? (d0 ? 0 : 4) + ((__ffs(dx) - 1) >> 3) : 8;
-        if (m == 8 && cap > 8) {
-            if (bestL > 8 && lds_u8(a + bestL) != lds_u8(xi + bestL)) continue;
-            m = 8 + lcp_capped(xsB, cur + 8, si + 8, cap - 8);
+        int m;
+        if (dx) {
+            m = min((d0 ? 0 : 4) + ((__ffs(dx) - 1) >> 3), cap);
+        } else {                                        // eight equal bytes
+            m = min(8, cap);
+            if (cap > 8) {
+                if (bestL > 8 && lds_u8(a + bestL) != lds_u8(xi + bestL)) continue;
+                m = 8 + lcp_capped(xsB, cur + 8, si + 8, cap - 8);
+            }
+            if (m <= bestL) continue;
         }
-        m = min(m, cap);
-        if (m > bestL) {
-            bestL = m; bestS = cur;
-            if (m == cap) break;                        // nothing nearer can beat the cap
-            const int nb = min(m, 7) + 1;               // now bytes 0..m must agree (all eight from m = 7 on)
-            const unsigned long long mk = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
-            mLo = (uint32_t)mk; mHi = (uint32_t)(mk >> 32);
-        }
+        bestL = m; bestS = cur;
+        if (m == cap) break;                            // nothing nearer can beat the cap
+        // now bytes 0..m must agree (all eight from m = 7 on): shifts that clamp at 32 build both mask words
+        const uint32_t sh8 = 8u * (uint32_t)min(m, 7) + 8u;      // 8 .. 64 mask bits
+        uint32_t t;
+        asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(0xFFFFFFFFu), "r"(sh8));            // 0 from 32 bits on
+        mLo = ~t;
+        asm("shr.b32 %0, %1, %2;" : "=r"(mHi) : "r"(0xFFFFFFFFu), "r"(64u - sh8));    // 0 up to 32 bits
     }
     bestLOut = bestL; bestSOut = bestS;
 }
