@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 __device__ __forceinline__ uint32_t lds_u32_unaligned(uint32_t a)
 {
     const uint32_t al = a & ~3u;
-    return __funnelshift_r(lds_u32(al), lds_u32(al + 4), (a & 3u) * 8);
+    return __funnelshift_r(lds_u32(al), lds_u32(al + 4), a * 8);      // the funnel shift wraps at 32: (a * 8) & 31 = (a & 3) * 8
 }
 
 // length of the common prefix of x[a..] and x[b..], at most cap.  Both streams are read as ALIGNED words with
@@ -108,7 +108,7 @@ __device__ __forceinline__ int lcp_capped(uint32_t xsA, int a, int b, int cap)
 {
     const uint32_t pa = xsA + (uint32_t)a, pb = xsA + (uint32_t)b;
     uint32_t aa = pa & ~3u, ab = pb & ~3u;
-    const uint32_t sa = (pa & 3u) * 8, sb = (pb & 3u) * 8;
+    const uint32_t sa = pa * 8, sb = pb * 8;            // wrapping funnel shifts: only (p & 3) * 8 counts
     uint32_t wa0 = lds_u32(aa), wb0 = lds_u32(ab);
     int k = 0;
     while (k < cap) {
@@ -150,11 +150,15 @@ __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, in
         if (s >= si) break;                             // chain exhausted (MT_NONE >= si as well)
         const int cur = s;
         s = (int)lds_u16(upB + 2 * cur);
-        const uint32_t a = xsB + cur, al = a & ~3u, sh = (a & 3u) * 8;
+        const uint32_t a = xsB + cur, al = a & ~3u, sh = a * 8;    // wrapping funnel shift: (a & 3) * 8
         const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4), w2 = lds_u32(al + 8);
-        const uint32_t d0 = __funnelshift_r(w0, w1, sh) ^ wsi0;
-        const uint32_t d1 = __funnelshift_r(w1, w2, sh) ^ wsi1;
-        if ((d0 & mLo) | (d1 & mHi)) continue;          // cannot beat the current best
+        const uint32_t c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh);
+        // (candidate ^ position) & mask in one LOP3 per word; the bare differences are only needed on improvement
+        uint32_t t0, t1;
+        asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t0) : "r"(c0), "r"(wsi0), "r"(mLo));
+        asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t1) : "r"(c1), "r"(wsi1), "r"(mHi));
+        if (t0 | t1) continue;                          // cannot beat the current best
+        const uint32_t d0 = c0 ^ wsi0, d1 = c1 ^ wsi1;
         // The candidate agrees on bytes 0..bestL (all eight once bestL >= 7): below eight bytes that IS a strict
         // improvement, no comparison needed (bestL < cap here, or the walk would have ended at the cap).
         const uint32_t dx = d0 ? d0 : d1;               // word holding the first differing byte
