@@ -360,11 +360,13 @@ k_enc_split(Ws ws, uint32_t nSeg, uint32_t G)
     __shared__ uint32_t running;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool inSmem = nSeg <= kPreSmem;
+    // a stream costs at most ~5e5 units: 4096 of them fit 32 bits as they are, larger batches are scaled down
+    const uint32_t scale = inSmem ? 0u : 7u;
     if (tid == 0) running = 0;
     __syncthreads();
     for (uint32_t base = 0; base < nSeg; base += 1024) {
         const uint32_t s = base + tid;
-        const uint32_t v = s < nSeg ? ws.segCost[s] : 0u;
+        const uint32_t v = s < nSeg ? (ws.segCost[s] >> scale) : 0u;
         uint32_t inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
