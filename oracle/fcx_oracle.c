@@ -452,6 +452,228 @@ uint64_t fcxo_decompress_file(const uint8_t *file, uint64_t nbytes, uint8_t *out
 }
 
 /* ------------------------------------------------------------------ */
+/* LZ78 / FCX8 block codec (scope row f-3, "next")      */
+/* ------------------------------------------------------------------ */
+/* Tokenizer, mc:1832-1899.  The reference keeps phrases in a map keyed by a BKDR hash and
+ * verifies with memcmp (mc:1758-1796), so the hash never shows in the output: the token list
+ * is plain LZ78 -- the longest known phrase, then one more byte, the new phrase taking the
+ * token's 1-based number.  Here the dictionary is a trie held in an open-addressing table
+ * keyed by (parent phrase, byte).  An input that ends inside a known phrase emits
+ * (phrase, 0x00) and adds nothing (mc:1858-1862). */
+uint32_t fcxo_lz78_tokenize(const uint8_t *x, uint32_t n, uint32_t *idx, uint8_t *c)
+{
+    if (n == 0) return 0;
+    uint32_t cap = 1;
+    while (cap < 2u * n + 16u) cap <<= 1;
+    uint64_t *key = (uint64_t *)malloc((size_t)cap * sizeof(uint64_t));   /* (parent << 8 | byte) + 1, 0 = empty */
+    uint32_t *val = (uint32_t *)malloc((size_t)cap * sizeof(uint32_t));
+    memset(key, 0, (size_t)cap * sizeof(uint64_t));
+    uint32_t T = 0, next = 1, cur = 0;
+    while (cur < n) {
+        uint32_t node = 0, k = 0;
+        uint32_t slot = 0;
+        while (cur + k < n) {
+            const uint64_t kk = (((uint64_t)node << 8) | x[cur + k]) + 1;
+            slot = (uint32_t)((kk * 0x9E3779B97F4A7C15ull) >> 40) & (cap - 1);
+            while (key[slot] && key[slot] != kk) slot = (slot + 1) & (cap - 1);
+            if (!key[slot]) break;                    /* phrase + this byte is new */
+            node = val[slot];
+            k++;
+        }
+        if (cur + k >= n) {                           /* ran out of input inside a known phrase (k >= 1) */
+            idx[T] = node; c[T] = 0; T++;
+            break;
+        }
+        key[slot] = (((uint64_t)node << 8) | x[cur + k]) + 1;
+        val[slot] = next++;                           /* mc:1878: ++dictIdx after every emitted token */
+        idx[T] = node; c[T] = x[cur + k]; T++;
+        cur += k + 1;
+    }
+    free(key); free(val);
+    return T;
+}
+
+/* create_huffman_tree (mc:535-617) for any number of leaves whose weights are ALL non-zero (the group
+ * tree: every group of 256 ranks holds at least one used index).  child[2j], child[2j+1] = children of
+ * internal node n + j; a value < n is a leaf.  Same two-queue rule as fcxo_huffman_tree. */
+static void tree_general(const uint32_t *w, uint32_t n, uint32_t *child)
+{
+    uint32_t *ord = (uint32_t *)malloc((size_t)n * sizeof(uint32_t));
+    uint32_t *tmp = (uint32_t *)malloc((size_t)n * sizeof(uint32_t));
+    uint64_t *iw = (uint64_t *)malloc((size_t)n * sizeof(uint64_t));
+    for (uint32_t i = 0; i < n; i++) ord[i] = i;
+    /* stable bottom-up merge sort by weight (the reference's merge sort takes the left run on '<=') */
+    for (uint32_t width = 1; width < n; width <<= 1) {
+        for (uint32_t lo = 0; lo < n; lo += 2 * width) {
+            uint32_t mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
+            uint32_t a = lo, b = mid, o = lo;
+            while (a < mid && b < hi) tmp[o++] = (w[ord[a]] <= w[ord[b]]) ? ord[a++] : ord[b++];
+            while (a < mid) tmp[o++] = ord[a++];
+            while (b < hi) tmp[o++] = ord[b++];
+        }
+        memcpy(ord, tmp, (size_t)n * sizeof(uint32_t));
+    }
+    uint32_t qa = 0, qb = 0, made = 0;
+    while ((n - qa) + (made - qb) > 1) {
+        uint64_t sum = 0;
+        for (int k = 0; k < 2; k++) {
+            int take_leaf;
+            if (qa >= n) take_leaf = 0;
+            else if (qb >= made) take_leaf = 1;
+            else take_leaf = (uint64_t)w[ord[qa]] <= iw[qb];
+            if (take_leaf) { child[2 * made + k] = ord[qa]; sum += w[ord[qa]]; qa++; }
+            else { child[2 * made + k] = n + qb; sum += iw[qb]; qb++; }
+        }
+        iw[made++] = sum;
+    }
+    free(ord); free(tmp); free(iw);
+}
+
+/* my_compress_file_lz78 (mc:3127-3476): one FCX8 block payload; returns bytes written.
+ *   u32 wCnt | u8 bitmap[maxIdx/8+1] | u32 groups | (groups-1) x {u32 left, u32 right} (groups > 1)
+ *   | u32 T | u32 W, u32 words[W] (groups > 1) | u8 posInGroup[T] | HuffSection(c[T]) */
+uint32_t fcxo_compress_block_lz78(const uint8_t *x, uint32_t n, uint8_t *out)
+{
+    if (n == 0) return 0;                              /* the reference is never called with an empty block */
+    uint32_t *idx = (uint32_t *)malloc((size_t)n * sizeof(uint32_t));
+    uint8_t *c = (uint8_t *)malloc(n);
+    const uint32_t T = fcxo_lz78_tokenize(x, n, idx, c);
+    uint32_t maxIdx = 0;
+    for (uint32_t t = 0; t < T; t++) if (idx[t] > maxIdx) maxIdx = idx[t];
+    const uint32_t mapB = maxIdx / 8 + 1;              /* mc:3182-3183 */
+    uint8_t *q = out;
+    uint8_t *bm = q + 4;
+    memset(bm, 0, mapB);
+    for (uint32_t t = 0; t < T; t++) bm[idx[t] >> 3] |= (uint8_t)(1u << (idx[t] & 7));   /* mc:3189-3192 */
+    /* rank of every used index among the used ones (the reference sorts the tokens and squeezes, mc:3159-3175) */
+    uint32_t *rank = (uint32_t *)malloc(((size_t)maxIdx + 1) * sizeof(uint32_t));
+    uint32_t wCnt = 0;
+    for (uint32_t v = 0; v <= maxIdx; v++) { rank[v] = wCnt; wCnt += (bm[v >> 3] >> (v & 7)) & 1; }
+    put_u32(q, wCnt); q += 4 + mapB;
+    const uint32_t groups = (wCnt + 255) / 256;        /* mc:3227-3229 */
+    put_u32(q, groups); q += 4;
+    uint32_t *gchild = NULL;
+    if (groups > 1) {
+        uint32_t *gw = (uint32_t *)calloc(groups, sizeof(uint32_t));
+        for (uint32_t t = 0; t < T; t++) gw[rank[idx[t]] >> 8]++;
+        gchild = (uint32_t *)malloc((size_t)2 * (groups - 1) * sizeof(uint32_t));
+        tree_general(gw, groups, gchild);
+        free(gw);
+        for (uint32_t j = 0; j < 2 * (groups - 1); j++) { put_u32(q, gchild[j]); q += 4; }   /* mc:3273-3287 */
+    }
+    put_u32(q, T); q += 4;                             /* mc:3321,3341 */
+    if (groups > 1) {
+        /* codes: root = last internal node, bit k of a code = k-th branch from the root, 0 = left (mc:2927-3006) */
+        uint32_t nint = groups - 1;
+        uint64_t *ibits = (uint64_t *)calloc(nint, sizeof(uint64_t));
+        uint32_t *ilen = (uint32_t *)calloc(nint, sizeof(uint32_t));
+        uint64_t *lbits = (uint64_t *)calloc(groups, sizeof(uint64_t));
+        uint32_t *llen = (uint32_t *)calloc(groups, sizeof(uint32_t));
+        int too_long = 0;
+        for (int64_t j = (int64_t)nint - 1; j >= 0; j--)
+            for (uint32_t side = 0; side < 2; side++) {
+                const uint32_t ci = gchild[2 * j + side];
+                const uint32_t d = ilen[j] + 1;
+                if (d > 64) { too_long = 1; continue; }
+                const uint64_t b = ibits[j] | ((uint64_t)side << ilen[j]);
+                if (ci < groups) { lbits[ci] = b; llen[ci] = d; }
+                else { ibits[ci - groups] = b; ilen[ci - groups] = d; }
+            }
+        uint64_t total = 0;
+        for (uint32_t t = 0; t < T; t++) total += llen[rank[idx[t]] >> 8];
+        const uint32_t W = (uint32_t)((total + 31) / 32);
+        put_u32(q, W); q += 4;
+        memset(q, 0, (size_t)W * 4);
+        uint64_t pos = 0;
+        for (uint32_t t = 0; t < T; t++) {
+            const uint32_t g = rank[idx[t]] >> 8;
+            for (uint32_t k = 0; k < llen[g]; k++, pos++)
+                if ((lbits[g] >> k) & 1) q[pos >> 3] |= (uint8_t)(1u << (pos & 7));
+        }
+        q += (size_t)W * 4;
+        free(ibits); free(ilen); free(lbits); free(llen); free(gchild);
+        if (too_long) { free(idx); free(c); free(rank); return UINT32_MAX; }   /* > 64-bit group code: not representable here */
+    }
+    for (uint32_t t = 0; t < T; t++) *q++ = (uint8_t)(rank[idx[t]] & 255);   /* mc:3355 */
+    q += fcxo_huffman_section(c, T, q);                /* mc:3384-3471 is the section builder of mc:1011-1091 again */
+    free(idx); free(c); free(rank);
+    return (uint32_t)(q - out);
+}
+
+/* my_decompress_file_lz78 (mc:3478-3710) + my_LZ78_decompress (mc:1901-1934); a trailing 0x00 is
+ * always dropped (mc:3701-3703).  Returns decoded bytes or UINT32_MAX. */
+uint32_t fcxo_decompress_block_lz78(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap)
+{
+    rd_t r = { payload, nbytes, 0 };
+    const uint32_t wCnt = rd_u32(&r);
+    if (wCnt == 0 || wCnt > (1u << 21)) return UINT32_MAX;
+    uint32_t *used = (uint32_t *)malloc((size_t)wCnt * sizeof(uint32_t));
+    uint32_t got = 0, v = 0;
+    const uint64_t bm0 = r.pos;
+    while (got < wCnt) {                                /* mc:3497-3503 */
+        if (bm0 + (v >> 3) >= nbytes) { free(used); return UINT32_MAX; }
+        if ((payload[bm0 + (v >> 3)] >> (v & 7)) & 1) used[got++] = v;
+        v++;
+    }
+    r.pos += used[wCnt - 1] / 8 + 1;
+    const uint32_t groups = rd_u32(&r);
+    uint32_t *gchild = NULL;
+    if (groups > 1) {
+        if (groups > (1u << 13)) { free(used); return UINT32_MAX; }
+        gchild = (uint32_t *)malloc((size_t)2 * (groups - 1) * sizeof(uint32_t));
+        for (uint32_t j = 0; j < 2 * (groups - 1); j++) gchild[j] = rd_u32(&r);
+    }
+    const uint32_t T = rd_u32(&r);
+    if (T == 0 || T > (1u << 21)) { free(used); free(gchild); return UINT32_MAX; }
+    uint32_t *grp = (uint32_t *)calloc(T, sizeof(uint32_t));
+    uint32_t rc = UINT32_MAX;
+    uint8_t *cs = NULL; uint32_t *start = NULL, *len = NULL;
+    if (groups > 1) {                                   /* mc:3008-3055 */
+        const uint32_t W = rd_u32(&r);
+        uint32_t node = groups - 2, j = 0;
+        for (uint32_t wi = 0; wi < W; wi++) {
+            const uint32_t word = rd_u32(&r);
+            for (uint32_t b = 0; b < 32 && j < T; b++) {
+                if (node >= groups - 1) goto done;
+                const uint32_t ci = gchild[2 * node + ((word >> b) & 1)];
+                if (ci < groups) { grp[j++] = ci; node = groups - 2; }
+                else node = ci - groups;
+            }
+        }
+    }
+    {
+        const uint64_t pos0 = r.pos;
+        r.pos += T;
+        cs = (uint8_t *)calloc(T, 1);
+        if (huff_section_decode(&r, cs, T) < 0) goto done;
+        start = (uint32_t *)malloc((size_t)T * sizeof(uint32_t));
+        len = (uint32_t *)malloc((size_t)T * sizeof(uint32_t));
+        uint32_t cur = 0;
+        for (uint32_t t = 0; t < T; t++) {
+            const uint32_t pg = pos0 + t < nbytes ? payload[pos0 + t] : 0;
+            const uint32_t ri = grp[t] * 256 + pg;
+            if (ri >= wCnt) goto done;
+            const uint32_t id = used[ri];
+            uint32_t l = 0, s0 = 0;
+            if (id) {                                   /* phrase id = token id-1 (mc:1921-1927) */
+                if (id > t) goto done;
+                l = len[id - 1]; s0 = start[id - 1];
+            }
+            if ((uint64_t)cur + l + 1 > out_cap) goto done;
+            for (uint32_t k = 0; k < l; k++) out[cur + k] = out[s0 + k];
+            out[cur + l] = cs[t];
+            start[t] = cur; len[t] = l + 1;
+            cur += l + 1;
+        }
+        if (cur && out[cur - 1] == 0) cur--;            /* mc:3701-3703 */
+        rc = cur;
+    }
+done:
+    free(used); free(gchild); free(grp); free(cs); free(start); free(len);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
 /* mc:1407-1443 Sunday search, for the in-source known answers         */
 /* ------------------------------------------------------------------ */
 int32_t fcxo_sunday_search(const uint8_t *m, int32_t mlen, const uint8_t *s, int32_t slen)

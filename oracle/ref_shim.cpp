@@ -150,6 +150,42 @@ uint64_t ref_compress_file(const uint8_t *x, uint64_t n, uint8_t *out)
     return (uint64_t)(q - out);
 }
 
+/* ---- LZ78 / FCX8 (scope row f-3).  The reference reports progress on std::cout (mc:3159 ...): muted here. */
+struct fcx_cout_mute {
+    std::streambuf *old;
+    fcx_cout_mute() : old(std::cout.rdbuf(nullptr)) {}
+    ~fcx_cout_mute() { std::cout.rdbuf(old); std::cout.clear(); }
+};
+
+uint32_t ref_lz78_tokenize(const uint8_t *x, uint32_t n, uint32_t *idx, uint8_t *c)
+{
+    std::vector<stLZ78CmpCp> v;
+    my_LZ78_compress((void *)x, n, &v);
+    for (size_t k = 0; k < v.size(); k++) { idx[k] = v[k].idx; c[k] = v[k].c; }
+    return (uint32_t)v.size();
+}
+
+uint32_t ref_compress_block_lz78(const uint8_t *x, uint32_t n, uint8_t *out)
+{
+    fcx_cout_mute mute;
+    return my_compress_file_lz78((void *)x, n, out);
+}
+
+uint32_t ref_decompress_block_lz78(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap)
+{
+    fcx_cout_mute mute;
+    uint8_t *buf = (uint8_t *)calloc(2u << 20, 1);
+    if (nbytes > (2u << 20)) { free(buf); return 0xffffffffu; }
+    memcpy(buf, payload, nbytes);
+    char *mem = NULL; size_t memlen = 0;
+    FILE *f = open_memstream(&mem, &memlen);
+    uint32_t got = my_decompress_file_lz78(buf, nbytes, f);
+    fclose(f);
+    if (memlen <= out_cap) memcpy(out, mem, memlen);
+    free(mem); free(buf);
+    return got;
+}
+
 uint32_t ref_sizeof_head(void) { return (uint32_t)sizeof(stCmpFileHead); }
 
 } /* extern "C" */

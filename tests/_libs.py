@@ -55,6 +55,10 @@ class _Codec:
         f("compress_block", C.c_uint32, [u8p, C.c_uint32, u8p])
         f("decompress_block", C.c_uint32, [u8p, C.c_uint32, u8p, C.c_uint32])
         f("compress_file", C.c_uint64, [u8p, C.c_uint64, u8p])
+        # LZ78 / FCX8 (scope row f-3): tokenizer, block payload, block decoder
+        f("lz78_tokenize", C.c_uint32, [u8p, C.c_uint32, u32p, u8p])
+        f("compress_block_lz78", C.c_uint32, [u8p, C.c_uint32, u8p])
+        f("decompress_block_lz78", C.c_uint32, [u8p, C.c_uint32, u8p, C.c_uint32])
 
     def _f(self, name, res, args):
         fn = getattr(self.lib, self.px + name)
@@ -116,6 +120,30 @@ class _Codec:
         x = _as_u8(payload)
         out = np.zeros(cap, np.uint8)
         k = self._decompress_block(_p8(x), len(x), _p8(out), cap)
+        if k == 0xFFFFFFFF:
+            return None
+        return out[:k].tobytes()
+
+    def lz78_tokenize(self, data):
+        x = _as_u8(data)
+        n = len(x)
+        idx = np.zeros(max(n, 1), np.uint32)
+        c = np.zeros(max(n, 1), np.uint8)
+        T = self._lz78_tokenize(_p8(x if n else np.zeros(1, np.uint8)), n, _p32(idx), _p8(c))
+        return idx[:T].copy(), c[:T].copy()
+
+    def compress_block_lz78(self, data):
+        x = _as_u8(data)
+        xin = np.zeros(max(2 << 20, len(x)), np.uint8)       # zero-initialised 2 MiB buffers, as the reference's caller (mc:4073,4088)
+        xin[: len(x)] = x
+        out = np.zeros(4 << 20, np.uint8)
+        k = self._compress_block_lz78(_p8(xin), len(x), _p8(out))
+        return out[:k].tobytes()
+
+    def decompress_block_lz78(self, payload, cap=(1 << 20) + 64):
+        x = _as_u8(payload)
+        out = np.zeros(cap, np.uint8)
+        k = self._decompress_block_lz78(_p8(x), len(x), _p8(out), cap)
         if k == 0xFFFFFFFF:
             return None
         return out[:k].tobytes()

@@ -68,3 +68,25 @@ def test_two_block_container_golden():
     blob = oracle().compress_file(data)
     assert len(blob) == f["bytes"] and hashlib.sha256(blob).hexdigest() == f["sha256"]
     assert oracle().decompress_file(blob, len(data)) == data.tobytes()
+
+
+def test_lz78_golden():
+    """LZ78 / FCX8 (scope row f-3): golden_lz78.json comes from the reference build (make_golden_lz78.py)."""
+    L = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_lz78.json")))
+    o = oracle()
+    for t in L["tokens"]:
+        idx, c = o.lz78_tokenize(np.frombuffer(bytes.fromhex(t["in_hex"]), np.uint8))
+        assert idx.tolist() == t["idx"] and c.tobytes().hex() == t["c_hex"], t["in_hex"]
+    for t in L["payload_hex"]:
+        p = o.compress_block_lz78(np.frombuffer(bytes.fromhex(t["in_hex"]), np.uint8))
+        assert p.hex() == t["fcx8_block_hex"], t["in_hex"]
+        assert o.decompress_block_lz78(p).hex() == t["ref_decodes_hex"], t["in_hex"]
+    for b in L["blocks"]:
+        x = datagen.gen_block(b["family"], b["n"], b["seed"], 0)
+        assert hashlib.sha256(x.tobytes()).hexdigest() == b["in_sha256"], "datagen drifted: regenerate golden"
+        idx, _ = o.lz78_tokenize(x)
+        assert len(idx) == b["tokens"] and hashlib.sha256(idx.tobytes()).hexdigest() == b["idx_sha256"], b
+        p = o.compress_block_lz78(x)
+        assert len(p) == b["payload_bytes"] and hashlib.sha256(p).hexdigest() == b["payload_sha256"], b
+        d = o.decompress_block_lz78(p)
+        assert len(d) == b["ref_decoded_bytes"] and (d == x.tobytes()) == b["ref_decodes_to_input"], b

@@ -142,3 +142,28 @@ def test_decoder_matches_reference_including_defects():
         want = r.decompress_block(payload)
         got = o.decompress_block(payload)
         assert got == want, data[:16]
+
+
+def test_lz78_tokens_payloads_and_decoder():
+    """LZ78 / FCX8 (scope row f-3, "next"): the oracle's trie tokenizer, block payload and block decoder
+    against the reference's hash-map tokenizer (mc:1832-1899), my_compress_file_lz78 (mc:3127-3476) and
+    my_decompress_file_lz78 (mc:3478-3710), incl. the dropped trailing 0x00 (App. B2)."""
+    from my_compress_b200 import datagen
+
+    o, r = oracle(), reference()
+    bufs = [(n, b) for n, b in small_buffers(seed=7) if len(b) > 0]
+    bufs.append(("zipf300k", datagen.zipf_block(300000, 2, 0)))          # > 256 used indices: group Huffman tree
+    bufs.append(("phrases200k", datagen.phrases_block(200000, 2, 0)))
+    bufs.append(("uniform200k", datagen.uniform_block(200000, 2, 0)))
+    bufs.append(("zeros70k", np.zeros(70000, np.uint8)))                 # ends inside a known phrase, decodes one 0x00 short
+    bufs.append(("endzero", np.frombuffer(b"abcabcabd\0", np.uint8)))
+    ntok = 0
+    for name, buf in bufs:
+        io, co = o.lz78_tokenize(buf)
+        ir, cr = r.lz78_tokenize(buf)
+        assert np.array_equal(io, ir) and np.array_equal(co, cr), name
+        ntok += len(io)
+        po, pr = o.compress_block_lz78(buf), r.compress_block_lz78(buf)
+        assert po == pr, name
+        assert o.decompress_block_lz78(pr) == r.decompress_block_lz78(pr), name
+    assert ntok > 150000
