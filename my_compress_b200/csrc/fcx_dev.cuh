@@ -71,7 +71,7 @@ struct Ws {
     uint8_t *chunkSlow;   // [maxChunks] 1 = codes > 16 bits or too dense for the stage: handled by k_encode_slow
     uint32_t *chunkBits;  // [maxChunks]
     uint32_t *chunkBitOff;// [maxChunks] bit offset inside the segment's code words
-    uint4 *chunkDesc;     // [maxChunks] everything k_encode needs for one chunk (see CD_* in fcx_huff.cu)
+    uint4 *chunkDesc;     // [maxChunks] everything k_encode_w needs for one chunk (see CD_* in fcx_huff.cu)
     uint32_t *segCost;    // [4*maxBlocks+1] estimated encode cost per stream, then its exclusive prefix sum
     uint32_t *encSplit;   // [kMaxEncCtas+1] first chunk of every k_encode_w CTA (cost-balanced contiguous ranges)
     uint64_t *blkOff;     // [maxBlocks+1] byte offset (in d_out) of each "u32 size|payload" record

@@ -14,7 +14,7 @@
 // Bit offsets come from scans, never from a serial bit loop: the histogram pass keeps one
 // 256-bin histogram per 8192-symbol chunk, so once code lengths exist the bit length of every
 // chunk is a 256-term dot product; a scan over chunks/sections/blocks then gives every chunk
-// its absolute bit position in the final container, and k_encode writes code words straight
+// its absolute bit position in the final container, and k_encode_w writes code words straight
 // into the container (the sections sit at odd byte offsets, so everything is addressed as one
 // little-endian bit stream over the 4-byte aligned output buffer).
 #include "fcx_dev.cuh"
@@ -278,7 +278,7 @@ k_chunk_bits(Ws ws)
 }
 
 // chunk bit offsets inside each stream (<= 128 chunks per stream: one thread per stream), and the
-// 16-byte descriptor k_encode reads per chunk (runs after k_block_layout: needs segBitBase)
+// 16-byte descriptor k_encode_w reads per chunk (runs after k_block_layout: needs segBitBase)
 #ifndef FCX_ENC_STAGE_WORDS
 #define FCX_ENC_STAGE_WORDS 3064      // tests build a variant with a tiny stage to exercise the dense path
 #endif
@@ -504,6 +504,10 @@ k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
 // =========================================================================================
 // encode: the HBM-bound kernel (algorithmic bytes = S_in + S_out)
 // =========================================================================================
+// Two generations live here.  k_encode (CTA per chunk, TMA prefetch, three barriers per chunk) is the earlier
+// one, kept selectable with FCX_ENCODE=cta for A/B runs; k_encode_w further down (warp per sub-chunk, no
+// barriers in the chunk loop) is what launch_huff_stage runs.  k_encode_slow takes the streams whose codes are
+// longer than 24 bits for both.
 // One CTA encodes a contiguous range of 8192-symbol chunks.  Each thread owns a run of 32
 // consecutive symbols (two 16-byte loads).  Pass 1 looks every symbol up once in a table that
 // is replicated 32x in shared memory (tab[sym*32 + lane]: bank == lane, conflict-free) and

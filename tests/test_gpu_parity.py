@@ -127,7 +127,7 @@ def test_huffman_section_bytes(dc):
 
 
 def test_huffman_encode_groups_and_chunk_edges(dc):
-    """k_encode picks 4 / 3 / 2 / 1 symbols per 32-bit insert by the stream's longest code (<= 8 / 10 /
+    """k_encode_w picks 4 / 3 / 2 / 1 symbols per 32-bit insert by the stream's longest code (<= 8 / 10 /
     16 / 24 bits; longer goes to k_encode_slow): Fibonacci weights over m symbols give a longest code
     of m-1 bits.  Lengths sit around the 32-symbol run and 8192-symbol chunk boundaries, where the
     ragged tail, the bulk-copy size and the descriptor batch change behaviour."""
