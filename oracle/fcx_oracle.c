@@ -436,7 +436,8 @@ uint64_t fcxo_decompress_file(const uint8_t *file, uint64_t nbytes, uint8_t *out
 {
     if (nbytes < 10) return UINT64_MAX;
     if (file[0] != 'F' || file[1] != 'C' || file[2] != 'X') return UINT64_MAX;   /* mc:4146-4152 */
-    if (file[3] != '7') return UINT64_MAX;                                        /* lz78 not on this path */
+    if (file[3] != '7' && file[3] != '8') return UINT64_MAX;                      /* mc:4153-4164: '7' = lz77, '8' = lz78 */
+    const int lz78 = file[3] == '8';
     uint16_t nb; memcpy(&nb, file + 8, 2);
     uint64_t pos = 10, cur = 0;
     for (uint32_t b = 0; b < nb; b++) {
@@ -444,7 +445,9 @@ uint64_t fcxo_decompress_file(const uint8_t *file, uint64_t nbytes, uint8_t *out
         uint32_t sz = get_u32(file + pos); pos += 4;
         if (pos + sz > nbytes) return UINT64_MAX;
         uint64_t room = out_cap - cur;
-        uint32_t got = fcxo_decompress_block(file + pos, sz, out + cur, room > 0xffffffffu ? 0xffffffffu : (uint32_t)room);
+        const uint32_t room32 = room > 0xffffffffu ? 0xffffffffu : (uint32_t)room;
+        uint32_t got = lz78 ? fcxo_decompress_block_lz78(file + pos, sz, out + cur, room32)
+                            : fcxo_decompress_block(file + pos, sz, out + cur, room32);
         if (got == UINT32_MAX) return UINT64_MAX;
         cur += got; pos += sz;
     }
@@ -671,6 +674,27 @@ uint32_t fcxo_decompress_block_lz78(const uint8_t *payload, uint32_t nbytes, uin
 done:
     free(used); free(gchild); free(grp); free(cs); free(start); free(len);
     return rc;
+}
+
+/* FCX8 container: the block loop of mc:4073-4136 with my_compress_file_lz78 per block (header byte '8',
+ * mc:4080-4081).  out needs 10 + blocks * (4 + ~2.2 MiB). */
+uint64_t fcxo_compress_file_lz78(const uint8_t *x, uint64_t n, uint8_t *out)
+{
+    uint64_t nb = (n + FCXO_BLOCK_BYTES - 1) / FCXO_BLOCK_BYTES;
+    out[0] = 'F'; out[1] = 'C'; out[2] = 'X'; out[3] = '8';
+    put_u32(out + 4, (uint32_t)n);
+    uint16_t nb16 = (uint16_t)nb;
+    memcpy(out + 8, &nb16, 2);
+    uint8_t *q = out + 10;
+    for (uint64_t b = 0; b < nb; b++) {
+        uint64_t off = b * FCXO_BLOCK_BYTES;
+        uint32_t len = (uint32_t)((n - off) < FCXO_BLOCK_BYTES ? (n - off) : FCXO_BLOCK_BYTES);
+        uint32_t sz = fcxo_compress_block_lz78(x + off, len, q + 4);
+        if (sz == UINT32_MAX) return UINT64_MAX;
+        put_u32(q, sz);
+        q += 4 + sz;
+    }
+    return (uint64_t)(q - out);
 }
 
 /* ------------------------------------------------------------------ */

@@ -175,6 +175,8 @@ class Oracle(_Codec):
         lib.fcxo_compress_blocks.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
         lib.fcxo_longest_match.restype = None
         lib.fcxo_longest_match.argtypes = [u8p, C.c_uint32, C.c_uint32, u32p, u32p]
+        lib.fcxo_compress_file_lz78.restype = C.c_uint64
+        lib.fcxo_compress_file_lz78.argtypes = [u8p, C.c_uint64, u8p]
 
     def huffman_tree(self, weights):
         w = np.ascontiguousarray(weights, dtype=np.uint32)
@@ -219,6 +221,15 @@ class Oracle(_Codec):
 
     def compress_bound(self, n):
         return int(self.lib.fcxo_compress_bound(n))
+
+    def compress_file_lz78(self, data):
+        """FCX8 container (the reference CLI's `-c <anything but lz77>`)."""
+        x = _as_u8(data)
+        nb = (len(x) + (1 << 20) - 1) >> 20
+        out = np.zeros(10 + nb * (4 + (3 << 20)) + 64, np.uint8)
+        k = self.lib.fcxo_compress_file_lz78(_p8(x if len(x) else np.zeros(1, np.uint8)), len(x), _p8(out))
+        assert k != 0xFFFFFFFFFFFFFFFF
+        return out[:k].tobytes()
 
 
 class Reference(_Codec):

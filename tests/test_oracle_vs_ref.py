@@ -167,3 +167,25 @@ def test_lz78_tokens_payloads_and_decoder():
         assert po == pr, name
         assert o.decompress_block_lz78(pr) == r.decompress_block_lz78(pr), name
     assert ntok > 150000
+
+
+def test_lz78_container_is_what_the_reference_cli_writes(tmp_path):
+    """FCX8 file level: the oracle's container equals the file the reference CLI writes with `-c lz78`
+    (mc:4073-4136), and both decoders give the same bytes back (one trailing 0x00 per block may be lost, App. B2)."""
+    import os
+    import subprocess
+
+    from _libs import REF_CLI
+    from my_compress_b200 import datagen
+
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/my_compress_ref not built")
+    data = np.concatenate([datagen.zipf_block(1 << 20, 9, 0), datagen.phrases_block(1 << 20, 9, 1), datagen.uniform_block(12345, 9, 2)])
+    src, cmp_, back = tmp_path / "in.bin", tmp_path / "out.fcx8", tmp_path / "back.bin"
+    src.write_bytes(data.tobytes())
+    subprocess.check_call([REF_CLI, "-i", str(src), "-o", str(cmp_), "-c", "lz78"], stdout=subprocess.DEVNULL)
+    blob = cmp_.read_bytes()
+    assert blob[:4] == b"FCX8"
+    assert oracle().compress_file_lz78(data) == blob
+    subprocess.check_call([REF_CLI, "-i", str(cmp_), "-o", str(back)], stdout=subprocess.DEVNULL)
+    assert oracle().decompress_file(blob, len(data) + 64) == back.read_bytes() == data.tobytes()
