@@ -57,6 +57,13 @@ int fcx_compress_block_lz77(const uint8_t *in, uint32_t n, uint8_t *out, uint32_
 int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_n,
                       uint32_t device_mask);
 
+/* The body of the block loop alone (mc:4090-4122) for a caller that streams a file through in pieces and
+ * writes the header itself, as the reference does (placeholder at mc:4078-4086, rewritten at mc:4128-4129):
+ * n bytes (every piece but the last a multiple of 1 MiB) -> their "u32 size | payload" records, no header.
+ * Concatenating the records of consecutive pieces behind a header gives the same file as one call. */
+int fcx_compress_records_lz77(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_n,
+                              uint32_t device_mask);
+
 /* Replaces my_decompress_file_lz77 (mc:2255, called at mc:4182) for one payload, and the
  * decompress branch of main() (mc:4138-4202) for a container.  Output is what the
  * reference's decoder produces, including its single-symbol-stream behaviour. */
@@ -64,13 +71,23 @@ int fcx_decompress_block_lz77(const uint8_t *payload, uint32_t nbytes, uint8_t *
                               uint32_t *out_n);
 int fcx_decompress_lz77(const uint8_t *file, uint64_t nbytes, uint8_t *out, uint64_t out_cap, uint64_t *out_n,
                         uint32_t device_mask);
+/* The record loop alone (mc:4162-4197): n_blocks consecutive "u32 size | payload" records, no header. */
+int fcx_decompress_records_lz77(const uint8_t *records, uint64_t nbytes, uint32_t n_blocks, uint8_t *out,
+                                uint64_t out_cap, uint64_t *out_n, uint32_t device_mask);
+
+/* Host buffers: any memory works, page-locked memory lets the copies run at full PCIe speed and overlap the
+ * kernels (the reference's fread/fwrite buffers, mc:4073 and mc:4088, are what these replace).  NULL on
+ * failure.  Pageable buffers are copied through the driver's staging area: correct, but slower. */
+void *fcx_host_alloc(uint64_t bytes);
+void fcx_host_free(void *p);
 
 /* ---- device-resident entry points (what the throughput metric times) --------------- */
 
 typedef struct fcx_ctx fcx_ctx;
 
-/* Workspace for batches of up to max_batch_blocks 1 MiB blocks on CUDA device `device`
- * (about 6.7 MiB of HBM per block).  stream: a cudaStream_t (0 = legacy default). */
+/* Workspace for batches of up to max_batch_blocks (1..1024) 1 MiB blocks on CUDA device `device`
+ * (about 6.7 MiB of HBM per block); longer inputs run as several batches on the same workspace.
+ * stream: a cudaStream_t (0 = legacy default). */
 int fcx_ctx_create(fcx_ctx **ctx, int device, uint32_t max_batch_blocks);
 void fcx_ctx_destroy(fcx_ctx *ctx);
 int fcx_ctx_set_stream(fcx_ctx *ctx, void *cuda_stream);
@@ -86,6 +103,13 @@ int fcx_compress_lz77_device(fcx_ctx *ctx, const uint8_t *d_in, uint64_t n, uint
                              uint32_t flags, uint64_t total_bytes_for_header, uint32_t total_blocks_for_header);
 /* Waits for the stream; *out_n = bytes written by the last fcx_compress_lz77_device call. */
 int fcx_ctx_finish(fcx_ctx *ctx, uint64_t *out_n);
+
+/* Device-resident twin of fcx_decompress_lz77's record loop (mc:4162-4197): the container (or any run of
+ * records) lies at d_file, rec_off[b] (host array) is the byte offset of block b's "u32 size | payload" record
+ * inside it, block b decodes to d_out + b MiB and its decoded length is returned in lens[b] (host array).
+ * d_file must be readable for 16 bytes beyond the last record.  Synchronous. */
+int fcx_decompress_lz77_device(fcx_ctx *ctx, const uint8_t *d_file, const uint64_t *rec_off, uint32_t n_blocks,
+                               uint8_t *d_out, uint32_t *lens);
 
 /* Kernel launches issued on this context since creation (bench.py's gpu_launches). */
 uint64_t fcx_ctx_launch_count(const fcx_ctx *ctx);
@@ -119,6 +143,10 @@ int fcx_probe_streams(fcx_ctx *ctx, const uint8_t *d_in, uint32_t n, uint32_t *T
 /* one Huffman section (mc:987-1104) of S device-resident bytes -> host bytes. */
 int fcx_probe_huffman_section(fcx_ctx *ctx, const uint8_t *d_src, uint32_t S, uint8_t *out, uint32_t out_cap,
                               uint32_t *out_n);
+
+/* Memory-safety probe for tests (no sanitizer on the GPU pool): every workspace array of a context lies between
+ * two 256-byte guard bands.  check = 0 paints them; check = 1 returns how many bands were written to since. */
+int fcx_ctx_debug_guards(fcx_ctx *ctx, int check);
 
 /* Corpus generator following RandM() of the reference's generator program
  * (随机数的生成.cpp:26-42) with time() pinned to `seed`: byte i = perm[i] & 0xFF. */

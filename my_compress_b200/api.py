@@ -33,8 +33,9 @@ class FcxStats(C.Structure):
 EXPORTS = [
     "fcx_last_error", "fcx_device_count", "fcx_compress_bound", "fcx_compress_block_lz77", "fcx_compress_lz77",
     "fcx_decompress_block_lz77", "fcx_decompress_lz77", "fcx_ctx_create", "fcx_ctx_destroy", "fcx_ctx_set_stream",
-    "fcx_compress_lz77_device", "fcx_ctx_finish", "fcx_ctx_launch_count", "fcx_ctx_stats", "fcx_ctx_enable_timing",
-    "fcx_ctx_stage_times", "fcx_probe_match", "fcx_probe_match_auto", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
+    "fcx_compress_lz77_device", "fcx_decompress_lz77_device", "fcx_ctx_finish", "fcx_ctx_launch_count", "fcx_ctx_stats", "fcx_ctx_enable_timing",
+    "fcx_ctx_stage_times", "fcx_compress_records_lz77", "fcx_decompress_records_lz77", "fcx_host_alloc", "fcx_host_free",
+    "fcx_ctx_debug_guards", "fcx_probe_match", "fcx_probe_match_auto", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
 ]
 
 
@@ -52,6 +53,12 @@ def lib():
     L.fcx_compress_bound.argtypes = [C.c_uint64]
     L.fcx_compress_block_lz77.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.fcx_compress_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.fcx_compress_records_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.fcx_decompress_records_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.fcx_host_alloc.restype = C.c_void_p
+    L.fcx_host_alloc.argtypes = [C.c_uint64]
+    L.fcx_host_free.restype = None
+    L.fcx_host_free.argtypes = [C.c_void_p]
     L.fcx_decompress_block_lz77.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.fcx_decompress_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
     L.fcx_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32]
@@ -60,12 +67,14 @@ def lib():
     L.fcx_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.fcx_compress_lz77_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32,
                                            C.c_uint64, C.c_uint32]
+    L.fcx_decompress_lz77_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fcx_ctx_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.fcx_ctx_launch_count.argtypes = [C.c_void_p]
     L.fcx_ctx_launch_count.restype = C.c_uint64
     L.fcx_ctx_stats.argtypes = [C.c_void_p, C.POINTER(FcxStats)]
     L.fcx_ctx_enable_timing.argtypes = [C.c_void_p, C.c_int]
     L.fcx_ctx_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.fcx_ctx_debug_guards.argtypes = [C.c_void_p, C.c_int]
     L.fcx_probe_match.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fcx_probe_match_auto.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fcx_probe_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
@@ -137,6 +146,45 @@ def compress(data, n_gpus=1):
     return out[: n.value].tobytes()
 
 
+def compress_records(data, n_gpus=1):
+    """The block loop alone (mc:4090-4122): records of ``data`` without the file header."""
+    x = _host_u8(data)
+    out = np.empty(compress_bound(len(x)), np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_compress_records_lz77(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+def decompress_records(records, n_blocks, n_gpus=1):
+    x = _host_u8(records)
+    out = np.empty(max(1, n_blocks) * (BLOCK_BYTES + 8), np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_decompress_records_lz77(x.ctypes.data, len(x), int(n_blocks), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+class PinnedBuffer:
+    """Page-locked host memory from fcx_host_alloc as a numpy uint8 array (``.array``)."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().fcx_host_alloc(int(nbytes))
+        if not self.ptr:
+            raise FcxError(-3, lib().fcx_last_error().decode("utf-8", "replace"))
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, _u8p), shape=(int(nbytes),))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().fcx_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def decompress_into(src, dst, n_gpus=1):
     """FCX7 container (numpy uint8) -> decoded bytes written into ``dst`` (numpy uint8, ideally pinned); returns byte count."""
     n = C.c_uint64(0)
@@ -154,6 +202,17 @@ def decompress(blob, n_gpus=1):
     n = C.c_uint64(0)
     _check(lib().fcx_decompress_lz77(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
     return out[: n.value].tobytes()
+
+
+def record_offsets(blob, n_blocks, start=0):
+    """Byte offsets of ``n_blocks`` consecutive 'u32 size | payload' records in ``blob`` (mc:4162-4174) and the end offset."""
+    x = _host_u8(blob)
+    offs = np.zeros(n_blocks, np.uint64)
+    pos = int(start)
+    for b in range(n_blocks):
+        offs[b] = pos
+        pos += 4 + int.from_bytes(x[pos : pos + 4].tobytes(), "little")
+    return offs, pos
 
 
 def datagen_randm(m, seed):
@@ -207,6 +266,21 @@ class DeviceCompressor:
             d_out = self.torch.empty(compress_bound(d_in.numel()), dtype=self.torch.uint8, device=d_in.device)
         self.compress_async(d_in, d_out, **kw)
         return d_out, self.finish()
+
+    def decompress(self, d_file, rec_off, d_out):
+        """Device-resident decode: block b of the records at ``rec_off`` (numpy uint64) -> d_out[b MiB:]; returns lens."""
+        rec = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        lens = np.zeros(len(rec), np.uint32)
+        _check(lib().fcx_decompress_lz77_device(self._ctx, C.c_void_p(d_file.data_ptr()), rec.ctypes.data, len(rec),
+                                                C.c_void_p(d_out.data_ptr()), lens.ctypes.data))
+        return lens
+
+    def guards(self, check):
+        """check=False paints the guard bands around every workspace array; check=True counts the overwritten ones."""
+        rc = lib().fcx_ctx_debug_guards(self._ctx, 1 if check else 0)
+        if rc < 0:
+            _check(rc)
+        return rc
 
     def launch_count(self):
         return int(lib().fcx_ctx_launch_count(self._ctx))

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfcx.so")
-SOURCES = ["fcx_api.cu", "fcx_match.cu", "fcx_parse.cu", "fcx_huff.cu", "fcx_decode.cu"]
+SOURCES = ["fcx_api.cu", "fcx_host.cu", "fcx_match.cu", "fcx_parse.cu", "fcx_huff.cu", "fcx_decode.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -25,16 +25,21 @@ def needs_build():
 CLI = os.path.join(HERE, "fcx_cli")
 
 
+CLI_SMALL = os.path.join(HERE, "fcx_cli_smallpiece")      # test-only: 2-block pieces
+
+
 def build_cli(force=False):
-    """The flag-compatible CLI (my_compress_b200/cli/fcx_cli.cpp) linked against libfcx.so."""
+    """The flag-compatible CLI (my_compress_b200/cli/fcx_cli.cpp) linked against libfcx.so, and a test
+    variant whose file pieces are 2 blocks so that small files walk the multi-piece pipeline."""
     src = os.path.join(HERE, "cli", "fcx_cli.cpp")
-    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
-        return CLI
-    cmd = ["g++", "-O2", "-std=c++17", src, "-o", CLI, "-L" + HERE, "-lfcx", "-Wl,-rpath,$ORIGIN"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("g++ failed building fcx_cli")
+    for exe, defs in ((CLI, []), (CLI_SMALL, ["-DFCX_CLI_PIECE_BLOCKS=2"])):
+        if not force and os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+            continue
+        cmd = ["g++", "-O2", "-std=c++17", "-pthread"] + defs + [src, "-o", exe, "-L" + HERE, "-lfcx", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed building " + os.path.basename(exe))
     return CLI
 
 

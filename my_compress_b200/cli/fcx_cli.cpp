@@ -1,71 +1,206 @@
 // fcx_cli -- flag-compatible stand-in for the reference CLI (SURVEY 8f "next" row 2):
-//     ./fcx_cli -i <in> [-o <out>] [-c lz77]        (mc:3992-4053: no -c => decompress, default out "./out")
-// The whole file goes through fcx_compress_lz77 / fcx_decompress_lz77 in one batched device pass
-// instead of the reference's block-at-a-time loop (mc:4090-4122); the bytes written are identical.
-// Unlike the reference it prints nothing but errors, and "-c <anything else>" (lz78) is refused.
+//     ./fcx_cli -i <in> [-o <out>] [-c lz77] [-g <gpus>]     (mc:3992-4053: no -c => decompress, default out "./out")
+//
+// Same file loop as the reference's main(), with the three steps of every iteration running side by side:
+//   compress   (mc:4073-4136)  placeholder header, then per piece  fread -> fcx_compress_records_lz77 -> fwrite,
+//                              header rewritten at the end (mc:4128-4129)
+//   decompress (mc:4138-4202)  header, then per piece  fread of whole records -> fcx_decompress_records_lz77 -> fwrite
+// A piece is 256 MiB of input (256 blocks; the reference's piece is one block).  A reader thread fills one
+// page-locked buffer while the GPU works on the other and a writer thread drains the previous result, so disk,
+// PCIe and kernels overlap; the bytes written are identical to the reference's.  Unlike the reference it prints
+// nothing but errors, and "-c <anything else>" (lz78) is refused.
 #include "../../include/fcx.h"
 
 #include <getopt.h>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
-#include <vector>
+#include <thread>
 
-static bool read_file(const char *path, std::vector<uint8_t> &buf)
+namespace {
+
+#ifndef FCX_CLI_PIECE_BLOCKS
+#define FCX_CLI_PIECE_BLOCKS 256         // tests build a variant with tiny pieces to walk the multi-piece path on small files
+#endif
+constexpr uint64_t kPieceBlocks = FCX_CLI_PIECE_BLOCKS;
+constexpr uint64_t kPieceBytes = kPieceBlocks * FCX_BLOCK_BYTES;
+
+// A slot travels reader -> worker -> writer -> reader.
+struct Slot {
+    uint8_t *in = nullptr, *out = nullptr;
+    uint64_t inBytes = 0, outBytes = 0;
+    uint32_t blocks = 0;
+    int state = 0;                      // 0 free, 1 filled, 2 processed
+    bool last = false;
+};
+
+struct Pipe {
+    std::mutex mu;
+    std::condition_variable cv;
+    Slot slot[2];
+    bool failed = false;
+    std::string err;
+    void fail(const std::string &m)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed) { failed = true; err = m; }
+        cv.notify_all();
+    }
+    // waits until slot k reaches `state` (false: the pipeline failed)
+    bool wait(int k, int state)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed || slot[k].state == state; });
+        return !failed;
+    }
+    void set(int k, int state)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        slot[k].state = state;
+        cv.notify_all();
+    }
+};
+
+// fill(slot) -> false at end of input;  work(slot);  drain(slot)
+template <class Fill, class Work, class Drain>
+bool run_pipeline(Pipe &p, Fill fill, Work work, Drain drain)
 {
-    FILE *f = fopen(path, "rb");
-    if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    buf.resize(n > 0 ? (size_t)n : 0);
-    bool ok = n <= 0 || fread(buf.data(), 1, (size_t)n, f) == (size_t)n;
-    fclose(f);
-    return ok;
+    std::thread reader([&] {
+        for (int k = 0;; k ^= 1) {
+            if (!p.wait(k, 0)) return;
+            Slot &s = p.slot[k];
+            s.last = !fill(s);
+            p.set(k, 1);
+            if (s.last) return;
+        }
+    });
+    std::thread writer([&] {
+        for (int k = 0;; k ^= 1) {
+            if (!p.wait(k, 2)) return;
+            Slot &s = p.slot[k];
+            const bool last = s.last;
+            if (!drain(s)) { p.fail("write failed"); return; }
+            p.set(k, 0);
+            if (last) return;
+        }
+    });
+    for (int k = 0;; k ^= 1) {
+        if (!p.wait(k, 1)) break;
+        Slot &s = p.slot[k];
+        const bool last = s.last;
+        if (!work(s)) { p.fail(std::string("fcx: ") + fcx_last_error()); break; }
+        p.set(k, 2);
+        if (last) break;
+    }
+    reader.join();
+    writer.join();
+    return !p.failed;
 }
+
+} // namespace
 
 int main(int argc, char **argv)
 {
-    if (argc != 3 && argc != 4 && argc != 5 && argc != 7) {           // mc:3992
-        fprintf(stderr, "usage: %s -i <input> [-o <output>] [-c lz77]\n", argv[0]);
+    if (argc != 3 && argc != 4 && argc != 5 && argc != 7 && argc != 9) {           // mc:3992 (+ "-g n")
+        fprintf(stderr, "usage: %s -i <input> [-o <output>] [-c lz77] [-g <gpus>]\n", argv[0]);
         return 255;
     }
     static struct option longOpts[] = {{"file_in", required_argument, nullptr, 'i'},
                                        {"file_out", optional_argument, nullptr, 'o'},
                                        {"compress", required_argument, nullptr, 'c'},
+                                       {"gpus", required_argument, nullptr, 'g'},
                                        {nullptr, 0, nullptr, 0}};
     std::string in, out = "./out", algo;                               // mc:4051-4053: default output name
     bool compress = false;
-    int opt;
-    while ((opt = getopt_long(argc, argv, "i:o:c:", longOpts, nullptr)) != -1) {
+    int gpus = 1, opt;
+    while ((opt = getopt_long(argc, argv, "i:o:c:g:", longOpts, nullptr)) != -1) {
         if (opt == 'i' && optarg) in = optarg;
         else if (opt == 'o' && optarg) out = optarg;
         else if (opt == 'c' && optarg) { algo = optarg; compress = true; }
+        else if (opt == 'g' && optarg) gpus = atoi(optarg);
     }
-    std::vector<uint8_t> src;
-    if (!read_file(in.c_str(), src)) { fprintf(stderr, "open: %s Fail!!\n", in.c_str()); return 255; }
-    std::vector<uint8_t> dst;
-    uint64_t produced = 0;
-    int rc;
+    if (compress && strncmp(algo.c_str(), "lz77", 4) != 0) {          // mc:4040-4043: anything else means lz78
+        fprintf(stderr, "only -c lz77 is on this path (lz78 containers are out of scope)\n");
+        return 255;
+    }
+    const int nd = fcx_device_count();
+    if (nd == 0) { fprintf(stderr, "fcx: no CUDA device (this path has no CPU fallback)\n"); return 255; }
+    gpus = gpus < 1 ? 1 : gpus > nd ? nd : gpus;
+    const uint32_t mask = gpus >= 32 ? 0xFFFFFFFFu : ((1u << gpus) - 1u);
+    FILE *fin = fopen(in.c_str(), "rb");
+    if (!fin) { fprintf(stderr, "open: %s Fail!!\n", in.c_str()); return 255; }       // mc:4058-4062
+    FILE *fout = fopen(out.c_str(), "wb");
+    if (!fout) { fprintf(stderr, "open: %s Fail!!\n", out.c_str()); fclose(fin); return 255; }
+
+    Pipe p;
+    const uint64_t inCap = compress ? kPieceBytes : fcx_compress_bound(kPieceBytes);
+    const uint64_t outCap = compress ? fcx_compress_bound(kPieceBytes) : kPieceBlocks * (uint64_t)(FCX_BLOCK_BYTES + 8);
+    for (Slot &s : p.slot) {
+        s.in = static_cast<uint8_t *>(fcx_host_alloc(inCap));
+        s.out = static_cast<uint8_t *>(fcx_host_alloc(outCap));
+        if (!s.in || !s.out) { fprintf(stderr, "fcx: %s\n", fcx_last_error()); return 255; }
+    }
+    bool ok = true;
+    uint64_t totalIn = 0, totalBlocks = 0;
+    auto drain = [&](Slot &s) { return s.outBytes == 0 || fwrite(s.out, 1, s.outBytes, fout) == s.outBytes; };
     if (compress) {
-        if (strncmp(algo.c_str(), "lz77", 4) != 0) {                   // mc:4040-4043: anything else means lz78
-            fprintf(stderr, "only -c lz77 is on this path (lz78 containers are out of scope)\n");
-            return 255;
+        uint8_t head[FCX_HEADER_BYTES] = {'F', 'C', 'X', '7', 0, 0, 0, 0, 0, 0};
+        ok = fwrite(head, 1, sizeof head, fout) == sizeof head;                  // placeholder, mc:4078-4086
+        if (ok) ok = run_pipeline(p,
+            [&](Slot &s) {                                                       // mc:4090: fread up to one piece
+                s.inBytes = fread(s.in, 1, kPieceBytes, fin);
+                totalIn += s.inBytes;
+                totalBlocks += (s.inBytes + FCX_BLOCK_BYTES - 1) / FCX_BLOCK_BYTES;
+                return s.inBytes == kPieceBytes;
+            },
+            [&](Slot &s) {
+                s.outBytes = 0;
+                return s.inBytes == 0 || fcx_compress_records_lz77(s.in, s.inBytes, s.out, outCap, &s.outBytes, mask) == FCX_OK;
+            },
+            drain);
+        if (ok) {                                                                // mc:4128-4129: the real header
+            const uint32_t tb = (uint32_t)totalIn;                               // uInt32 cmp_before_bytes wraps (mc:105)
+            const uint16_t bn = (uint16_t)totalBlocks;                           // uInt16 block_num wraps (mc:106)
+            memcpy(head + 4, &tb, 4); memcpy(head + 8, &bn, 2);
+            ok = fseek(fout, 0, SEEK_SET) == 0 && fwrite(head, 1, sizeof head, fout) == sizeof head;
         }
-        dst.resize(fcx_compress_bound(src.size()));
-        rc = fcx_compress_lz77(src.data(), src.size(), dst.data(), dst.size(), &produced, 0);
     } else {
-        if (src.size() < FCX_HEADER_BYTES) { fprintf(stderr, "Read file head infomation error!!!\n"); return 255; }
+        uint8_t head[FCX_HEADER_BYTES];
+        if (fread(head, 1, sizeof head, fin) != sizeof head) { fprintf(stderr, "Read file head infomation error!!!\n"); return 255; }   // mc:4139-4144
+        if (memcmp(head, "FCX", 3) != 0 || head[3] != '7') { fprintf(stderr, "not an FCX7 file\n"); return 255; }                     // mc:4146-4152
         uint16_t blocks;
-        memcpy(&blocks, src.data() + 8, 2);
-        dst.resize((size_t)(blocks ? blocks : 1) * (FCX_BLOCK_BYTES + 8));
-        rc = fcx_decompress_lz77(src.data(), src.size(), dst.data(), dst.size(), &produced, 0);
+        memcpy(&blocks, head + 8, 2);
+        uint32_t left = blocks;
+        ok = run_pipeline(p,
+            [&](Slot &s) {                                                       // mc:4162-4174: whole records, up to one piece
+                s.inBytes = 0; s.blocks = 0;
+                while (left && s.blocks < kPieceBlocks) {
+                    uint32_t sz;
+                    if (fread(&sz, 1, 4, fin) != 4) { p.fail("truncated record header"); return false; }
+                    if (s.inBytes + 4 + (uint64_t)sz > inCap) {
+                        if (s.blocks == 0) { p.fail("record larger than any valid block payload"); return false; }
+                        fseek(fin, -4, SEEK_CUR);                                // does not fit this piece: next one
+                        break;
+                    }
+                    memcpy(s.in + s.inBytes, &sz, 4);
+                    if (fread(s.in + s.inBytes + 4, 1, sz, fin) != sz) { p.fail("truncated record"); return false; }
+                    s.inBytes += 4 + (uint64_t)sz;
+                    s.blocks++; left--;
+                }
+                return left != 0;
+            },
+            [&](Slot &s) {
+                s.outBytes = 0;
+                return s.blocks == 0 || fcx_decompress_records_lz77(s.in, s.inBytes, s.blocks, s.out, outCap, &s.outBytes, mask) == FCX_OK;
+            },
+            drain);
     }
-    if (rc != FCX_OK) { fprintf(stderr, "fcx error %d: %s\n", rc, fcx_last_error()); return 255; }
-    FILE *f = fopen(out.c_str(), "wb");
-    if (!f) { fprintf(stderr, "open: %s Fail!!\n", out.c_str()); return 255; }
-    if (produced) fwrite(dst.data(), 1, produced, f);
-    fclose(f);
-    return 0;
+    if (!ok) fprintf(stderr, "%s\n", p.failed ? p.err.c_str() : "write failed");
+    for (Slot &s : p.slot) { fcx_host_free(s.in); fcx_host_free(s.out); }
+    fclose(fin);
+    if (fclose(fout) != 0) ok = false;
+    return ok ? 0 : 255;
 }

@@ -5,36 +5,12 @@
 // "u32 size | payload" record per block behind a 10-byte header.  Blocks share no state, so
 // a multi-GPU call simply gives each device a contiguous block range; the only cross-device
 // datum is each shard's byte count, needed to place its records in the output (host prefix sum).
-#include "../../include/fcx.h"
-#include "fcx_dev.cuh"
+#include "fcx_internal.h"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
-#include <string>
-#include <thread>
-#include <vector>
-
-namespace fcx {
-// fcx_match.cu
-void launch_match(const uint8_t *in, const uint32_t *blkLen, uint8_t *lenCode, uint16_t *dist, uint32_t nBlocks,
-                  uint32_t maxLen, bool forceEager, cudaStream_t st);
-void match_init();
-// fcx_parse.cu
-int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32_t nBlocks, uint32_t maxLen, cudaStream_t st);
-void parse_init();
-// fcx_huff.cu
-void huff_init();
-int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
-                      uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
-                      cudaStream_t st, void (*mark)(void *, int), void *markArg);
-// fcx_decode.cu
-int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out,
-                  uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st);
-size_t decode_scratch_per_block();
-} // namespace fcx
 
 using namespace fcx;
 
@@ -42,15 +18,11 @@ using namespace fcx;
 // errors
 // -----------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+namespace fcx {
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+const std::string &last_error_string() { return g_err; }
+} // namespace fcx
 extern "C" const char *fcx_last_error(void) { return g_err.c_str(); }
-
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess)                                                                     \
-            return fail(FCX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
-    } while (0)
 
 extern "C" int fcx_device_count(void)
 {
@@ -70,39 +42,61 @@ extern "C" uint64_t fcx_compress_bound(uint64_t n)
 // -----------------------------------------------------------------------------------------
 // context
 // -----------------------------------------------------------------------------------------
-enum { ST_MATCH = 0, ST_PARSE, ST_PLAN, ST_HIST, ST_TREE, ST_LAYOUT, ST_ENCODE, ST_ENCODE_SLOW, ST_HEADERS, ST_COUNT };
 static const char *kStageNames[ST_COUNT] = {"match", "parse", "plan", "hist", "tree", "layout", "encode", "encode_slow", "headers"};
 
-struct fcx_ctx {
-    int device = 0;
-    int numSM = 148;
-    cudaStream_t stream = 0;
-    uint32_t maxBlocks = 0;
-    uint32_t batchBlocks = 0;          // blocks per device batch (<= maxBlocks); 0 = maxBlocks
-    Ws ws{};
-    std::vector<void *> allocs;
-    uint64_t launches = 0;
-    // timing
-    bool timing = false;
-    std::vector<cudaEvent_t> ev;       // per call: ST_COUNT+1 events per batch
-    std::vector<int> evStage;
-    float stageMs[ST_COUNT] = {0};
-    // last call
-    bool pending = false;
-    uint64_t lastBytes = 0;
-    // decode scratch
-    uint8_t *decScratch = nullptr;
-    uint64_t *decRecOff = nullptr;
-    uint32_t *decOutLen = nullptr;
-};
+constexpr size_t kStatusBytes = C_WORDS * sizeof(uint64_t) + TOT_WORDS * sizeof(uint32_t);
+static_assert(TOT_WORDS % 2 == 0, "totals follow the 64-bit counters in one allocation");
 
+// Every workspace array sits between two 256-byte guard bands (fcx_ctx_debug_guards paints / checks them:
+// compute-sanitizer is not available on the GPU pool, so a test does the out-of-bounds-write check itself).
+constexpr size_t kGuard = 256;
 template <typename T>
 static cudaError_t dalloc(fcx_ctx *c, T **p, size_t count)
 {
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
-    if (e == cudaSuccess) { c->allocs.push_back(q); *p = reinterpret_cast<T *>(q); }
+    const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&q, bytes + 2 * kGuard);
+    if (e == cudaSuccess) {
+        c->allocs.push_back(q);
+        c->guardAt.push_back(static_cast<uint8_t *>(q));
+        c->guardAt.push_back(static_cast<uint8_t *>(q) + kGuard + bytes);
+        *p = reinterpret_cast<T *>(static_cast<uint8_t *>(q) + kGuard);
+    }
     return e;
+}
+
+extern "C" int fcx_ctx_debug_guards(fcx_ctx *c, int check)
+{
+    if (!c) return fail(FCX_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    int bad = 0;
+    std::vector<uint8_t> h(kGuard);
+    for (uint8_t *g : c->guardAt) {
+        if (!check) { CK(cudaMemset(g, 0xA5, kGuard)); continue; }
+        CK(cudaMemcpy(h.data(), g, kGuard, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < kGuard; i++) if (h[i] != 0xA5) { bad++; break; }
+    }
+    return bad;                                             // bands written to since they were painted
+}
+
+// Zeroes out[cursor .. cursor + bytes) (clamped to cap), starting at the first 16-byte unit that begins at or
+// after the cursor: the bytes before it were zeroed as the previous batch's slack (a bound ends >= 64 bytes
+// beyond anything a batch writes).
+__global__ void __launch_bounds__(256) k_zero_batch(uint8_t *out, const uint64_t *cursor, uint64_t bytes, uint64_t cap)
+{
+    const uint64_t cur = *cursor;
+    const uint64_t beg = (cur + 15) & ~15ull;
+    const uint64_t end = min(cap, cur + bytes);
+    if (beg >= end) return;
+    const uint64_t nVec = (end - beg) >> 4;
+    uint4 *v = reinterpret_cast<uint4 *>(out + beg);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nVec; i += stride) v[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0) {
+        const uint64_t t0 = beg + (nVec << 4);
+        if (t0 + threadIdx.x < end && threadIdx.x < 16) out[t0 + threadIdx.x] = 0;
+    }
 }
 
 __global__ void k_set_blklen(uint32_t *blkLen, uint64_t n, uint32_t firstBlock, uint32_t nb)
@@ -116,7 +110,10 @@ __global__ void k_set_blklen(uint32_t *blkLen, uint64_t n, uint32_t firstBlock, 
 
 extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks)
 {
-    if (!out || maxBatchBlocks == 0 || maxBatchBlocks > 65535) return fail(FCX_ERR_ARG, "fcx_ctx_create: bad arguments");
+    // a batch holds at most kMaxBatchBlocks blocks: chunk descriptors carry the stream id b*4+k in 12 bits and
+    // stream arena offsets are 32-bit (fcx_huff.cu); larger inputs run as several batches on the same context
+    if (!out || maxBatchBlocks == 0 || maxBatchBlocks > kMaxBatchBlocks)
+        return fail(FCX_ERR_ARG, "fcx_ctx_create: max_batch_blocks must be 1..1024");
     int nd = fcx_device_count();
     if (nd == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
     if (device < 0 || device >= nd) return fail(FCX_ERR_ARG, "fcx_ctx_create: no such device");
@@ -156,19 +153,21 @@ extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks
     A(dalloc(c, &w.segCost, B * 4 + 1));
     A(dalloc(c, &w.encSplit, (size_t)kMaxEncCtas + 1));
     A(dalloc(c, &w.blkOff, B + 1));
-    A(dalloc(c, &w.totals, (size_t)TOT_WORDS));
-    A(dalloc(c, &w.counters, (size_t)C_WORDS));
+    // counters (u64[C_WORDS]) and totals (u32[TOT_WORDS]) share one allocation: fcx_ctx_finish reads both at once
+    A(dalloc(c, &w.counters, (size_t)C_WORDS + TOT_WORDS / 2));
+    w.totals = reinterpret_cast<uint32_t *>(w.counters + C_WORDS);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&c->hostStatus), kStatusBytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMemset(w.counters, 0, kStatusBytes);
+    if (e == cudaSuccess) { match_init(); parse_init(); huff_init(); decode_init(); e = cudaGetLastError(); }
     if (e != cudaSuccess) {
         for (void *p : c->allocs) cudaFree(p);
+        if (c->hostStatus) cudaFreeHost(c->hostStatus);
+    if (c->decScratch) cudaFree(c->decScratch);
+    if (c->decRec) cudaFree(c->decRec);
+    if (c->decLen) cudaFree(c->decLen);
         delete c;
-        return fail(FCX_ERR_CUDA, std::string("workspace allocation: ") + cudaGetErrorString(e));
+        return fail(FCX_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
     }
-    cudaMemset(w.totals, 0, TOT_WORDS * sizeof(uint32_t));
-    cudaMemset(w.counters, 0, C_WORDS * sizeof(uint64_t));
-    match_init();
-    parse_init();
-    huff_init();
-    CK(cudaGetLastError());
     *out = c;
     return FCX_OK;
 }
@@ -180,9 +179,7 @@ extern "C" void fcx_ctx_destroy(fcx_ctx *c)
     cudaStreamSynchronize(c->stream);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (void *p : c->allocs) cudaFree(p);
-    if (c->decScratch) cudaFree(c->decScratch);
-    if (c->decRecOff) cudaFree(c->decRecOff);
-    if (c->decOutLen) cudaFree(c->decOutLen);
+    if (c->hostStatus) cudaFreeHost(c->hostStatus);
     delete c;
 }
 
@@ -238,28 +235,13 @@ extern "C" int fcx_ctx_stage_times(fcx_ctx *c, const char **names, float *ms, in
 // -----------------------------------------------------------------------------------------
 // device-resident compress
 // -----------------------------------------------------------------------------------------
-// Optional per-batch hooks of the host-buffer path: batch k starts only after waitBefore[k]
-// (its H2D copy), and when it is done the running output cursor is copied to hostCursor[k]
-// (pinned) and recordAfter[k] fires, so the host can start that batch's D2H while batch k+1 runs.
-struct BatchHooks {
-    cudaEvent_t *waitBefore = nullptr;
-    cudaEvent_t *recordAfter = nullptr;
-    uint64_t *hostCursor = nullptr;
-    const uint32_t *sizes = nullptr;        // blocks per batch (uneven pipeline plan); null = the context's uniform step
-    uint32_t nSizes = 0;
-};
-
-static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out, uint64_t outCap, uint32_t flags,
-                       uint64_t hdrBytes, uint32_t hdrBlocks, const BatchHooks *hooks = nullptr)
+int fcx::run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out, uint64_t outCap, uint32_t flags,
+                     uint64_t hdrBytes, uint32_t hdrBlocks, const BatchHooks *hooks)
 {
     const Ws &w = c->ws;
     cudaStream_t st = c->stream;
     const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
-    // edge words of every chunk are merged with atomicOr, so the destination starts out zero
-    const uint64_t zeroBytes = std::min<uint64_t>(outCap, fcx_compress_bound(n));
-    CK(cudaMemsetAsync(d_out, 0, zeroBytes, st));
-    CK(cudaMemsetAsync(w.totals, 0, TOT_WORDS * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(w.counters, 0, C_WORDS * sizeof(uint64_t), st));
+    CK(cudaMemsetAsync(w.counters, 0, kStatusBytes, st));           // counters + totals
     if (nBlocks == 0) {
         if (flags & FCX_WITH_HEADER) {
             // empty input: header only, block_num = 0
@@ -267,11 +249,10 @@ static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_o
             uint32_t tb = (uint32_t)hdrBytes; uint16_t bn = (uint16_t)hdrBlocks;
             memcpy(h + 4, &tb, 4); memcpy(h + 8, &bn, 2);
             if (outCap < 10) return fail(FCX_ERR_CAPACITY, "output buffer too small");
+            const uint64_t ten = 10;
             CK(cudaMemcpyAsync(d_out, h, 10, cudaMemcpyHostToDevice, st));
-            CK(cudaStreamSynchronize(st));
-            uint64_t ten = 10;
             CK(cudaMemcpyAsync(w.counters + C_CURSOR, &ten, 8, cudaMemcpyHostToDevice, st));
-            CK(cudaStreamSynchronize(st));
+            CK(cudaStreamSynchronize(st));                              // h / ten are stack variables
         }
         return FCX_OK;
     }
@@ -287,10 +268,13 @@ static int run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_o
         const uint32_t maxLen = (uint32_t)std::min<uint64_t>(rem, kBlockBytes);
         const uint32_t withHeader = (first == 0 && (flags & FCX_WITH_HEADER)) ? 1u : 0u;
         mark_stage(c, -1);
+        // edge words of every chunk are merged with atomicOr, so the part of the destination this batch can
+        // reach starts out zero (the running cursor lives on the device: the kernel reads it there)
+        k_zero_batch<<<c->numSM * 4, 256, 0, st>>>(d_out, w.counters + C_CURSOR, fcx_compress_bound((uint64_t)nb * kBlockBytes), outCap);
         k_set_blklen<<<(nb + 255) / 256, 256, 0, st>>>(w.blkLen, n, (uint32_t)first, nb);
         launch_match(bin, w.blkLen, w.lenCode, w.dist, nb, maxLen, false, st);
         mark_stage(c, ST_MATCH);
-        c->launches += 2 + launch_parse(bin, w.blkLen, w, nb, maxLen, st);
+        c->launches += 3 + launch_parse(bin, w.blkLen, w, nb, maxLen, st);
         mark_stage(c, ST_PARSE);
         c->launches += launch_huff_stage(w, nb, d_out, outCap, withHeader, (uint32_t)hdrBytes, hdrBlocks, 0, c->numSM, st,
                                          mark_stage, c);
@@ -318,12 +302,12 @@ extern "C" int fcx_ctx_finish(fcx_ctx *c, uint64_t *outN)
 {
     if (!c) return fail(FCX_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
+    // one pinned read of counters + totals on the context's own stream (no device-wide synchronisation)
+    CK(cudaMemcpyAsync(c->hostStatus, c->ws.counters, kStatusBytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (c->timing) collect_timing(c);
-    uint64_t counters[C_WORDS];
-    uint32_t totals[TOT_WORDS];
-    CK(cudaMemcpy(counters, c->ws.counters, sizeof(counters), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(totals, c->ws.totals, sizeof(totals), cudaMemcpyDeviceToHost));
+    const uint64_t *counters = c->hostStatus;
+    const uint32_t *totals = reinterpret_cast<const uint32_t *>(c->hostStatus + C_WORDS);
     c->pending = false;
     c->lastBytes = counters[C_CURSOR];
     if (outN) *outN = counters[C_CURSOR];
@@ -336,9 +320,9 @@ extern "C" int fcx_ctx_stats(fcx_ctx *c, fcx_stats *s)
 {
     if (!c || !s) return fail(FCX_ERR_ARG, "null pointer");
     CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->hostStatus, c->ws.counters, kStatusBytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    uint64_t counters[C_WORDS];
-    CK(cudaMemcpy(counters, c->ws.counters, sizeof(counters), cudaMemcpyDeviceToHost));
+    const uint64_t *counters = c->hostStatus;
     s->s_in = counters[C_SIN]; s->s_out = counters[C_SOUT];
     s->tokens = counters[C_TOKENS]; s->matches = counters[C_MATCHES];
     s->container_bytes = counters[C_CURSOR]; s->blocks = counters[C_BLOCKS];
@@ -346,316 +330,33 @@ extern "C" int fcx_ctx_stats(fcx_ctx *c, fcx_stats *s)
 }
 
 // -----------------------------------------------------------------------------------------
-// host-buffer entry points
+// device-resident decompress
 // -----------------------------------------------------------------------------------------
-namespace {
-struct DevSlot {
-    std::mutex mu;
-    fcx_ctx *ctx = nullptr;
-    uint32_t ctxBlocks = 0;
-    uint8_t *dIn = nullptr, *dOut = nullptr;
-    uint64_t inCap = 0, outCap = 0;
-    cudaStream_t stream = nullptr;          // kernels
-    cudaStream_t h2d = nullptr, d2h = nullptr;
-    std::vector<cudaEvent_t> evIn, evOut;   // per sub-batch
-    uint64_t *hostCursor = nullptr;         // pinned, per sub-batch
-    // decoder scratch (grow-only)
-    uint8_t *decScratch = nullptr; uint64_t decScratchCap = 0;
-    uint64_t *decRec = nullptr; uint32_t *decLen = nullptr; uint32_t decBlocks = 0;
-};
-DevSlot g_slots[64];
-constexpr uint32_t kMaxPipeBatches = 64;
-
-// grow-only per-device scratch for the host-buffer API
-int slot_prepare(DevSlot &s, int dev, uint64_t inBytes, uint64_t outBytes)
+extern "C" int fcx_decompress_lz77_device(fcx_ctx *c, const uint8_t *d_file, const uint64_t *recOff, uint32_t nBlocks,
+                                          uint8_t *d_out, uint32_t *lens)
 {
-    CK(cudaSetDevice(dev));
-    const uint64_t blocks = std::max<uint64_t>(1, (inBytes + kBlockBytes - 1) / kBlockBytes);
-    const uint32_t want = (uint32_t)std::min<uint64_t>(blocks, 1024);
-    if (!s.stream) {
-        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&s.h2d, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking));
-        CK(cudaHostAlloc(reinterpret_cast<void **>(&s.hostCursor), kMaxPipeBatches * sizeof(uint64_t), cudaHostAllocDefault));
-        s.evIn.resize(kMaxPipeBatches); s.evOut.resize(kMaxPipeBatches);
-        for (uint32_t k = 0; k < kMaxPipeBatches; k++) {
-            CK(cudaEventCreateWithFlags(&s.evIn[k], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&s.evOut[k], cudaEventDisableTiming));
-        }
-    }
-    if (!s.ctx || s.ctxBlocks < want) {
-        if (s.ctx) fcx_ctx_destroy(s.ctx);
-        s.ctx = nullptr;
-        int rc = fcx_ctx_create(&s.ctx, dev, want);
-        if (rc) return rc;
-        s.ctxBlocks = want;
-        fcx_ctx_set_stream(s.ctx, s.stream);
-    }
-    if (s.inCap < inBytes) {
-        if (s.dIn) cudaFree(s.dIn);
-        s.dIn = nullptr; s.inCap = 0;
-        CK(cudaMalloc(&s.dIn, inBytes + 256));
-        s.inCap = inBytes;
-    }
-    if (s.outCap < outBytes) {
-        if (s.dOut) cudaFree(s.dOut);
-        s.dOut = nullptr; s.outCap = 0;
-        CK(cudaMalloc(&s.dOut, outBytes + 256));
-        s.outCap = outBytes;
-    }
-    return FCX_OK;
-}
-} // namespace
-
-extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, uint64_t *outN,
-                                 uint32_t deviceMask)
-{
-    if (!out || !outN || (!in && n)) return fail(FCX_ERR_ARG, "null pointer");      // mc:2122-2123 returns 0 here
-    const int nd = fcx_device_count();
-    if (nd == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
-    std::vector<int> devs;
-    if (deviceMask == 0) deviceMask = 1;
-    for (int g = 0; g < 32 && g < nd; g++) if (deviceMask & (1u << g)) devs.push_back(g);
-    if (devs.empty()) return fail(FCX_ERR_ARG, "device_mask selects no visible device");
-    const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
-    if (outCap < 10) return fail(FCX_ERR_CAPACITY, "output buffer too small");
-    const size_t G = std::min<uint64_t>(devs.size(), std::max<uint64_t>(1, nBlocks));
-    std::vector<uint64_t> b0(G + 1);
-    for (size_t g = 0; g <= G; g++) b0[g] = nBlocks * g / G;                        // contiguous block ranges
-    std::vector<uint64_t> bytes(G, 0);
-    std::vector<int> rcs(G, FCX_OK);
-    std::vector<std::string> errs(G);
-    // One shard = one device.  The shard is cut into sub-batches so that the H2D copy of batch k+1
-    // and (single-device calls) the D2H copy of batch k-1 overlap the kernels of batch k.
-    const bool streamOut = (G == 1);
-    auto shard = [&](size_t g) {
-        DevSlot &s = g_slots[devs[g]];
-        std::lock_guard<std::mutex> lk(s.mu);
-        const uint64_t off = b0[g] * (uint64_t)kBlockBytes;
-        const uint64_t len = std::min<uint64_t>(n, b0[g + 1] * (uint64_t)kBlockBytes) - std::min<uint64_t>(n, off);
-        const uint64_t bound = fcx_compress_bound(len);
-        int rc = slot_prepare(s, devs[g], len, bound);
-        if (rc) { rcs[g] = rc; errs[g] = g_err; return; }
-        const uint64_t blocks = (len + kBlockBytes - 1) / kBlockBytes;
-        // Pipeline plan.  Only the first batch's upload and the last batch's download are exposed, so both
-        // are small; H2D runs ~3x faster than the kernels, so the second batch can already be five times the
-        // first, and the rest goes in a few large batches (every batch pays ~0.15 ms of latency-bound kernels).
-#ifndef FCX_PIPE_MIN_BLOCKS
-#define FCX_PIPE_MIN_BLOCKS 16
-#endif
-        std::vector<uint32_t> plan;
-        if (blocks > FCX_PIPE_MIN_BLOCKS) {
-            const uint32_t B = (uint32_t)blocks, cap = s.ctxBlocks;
-            const uint32_t edge = std::min<uint32_t>(16, std::max<uint32_t>(2, B / 16));
-            uint32_t rem = B - 2 * edge;
-            plan.push_back(edge);
-            const uint32_t second = std::min<uint32_t>(rem, 4 * edge + 4);
-            if (second) plan.push_back(second);
-            rem -= second;
-            // large inputs taper at the end as well: the download of a big batch would otherwise outlast the
-            // small last batch it is meant to hide behind (incompressible data downloads as much as it uploads)
-            const uint32_t taper = (B >= 256 && rem > second) ? second : 0;
-            rem -= taper;
-            if (rem) {
-                const uint32_t lim = std::min<uint32_t>(cap, B >= 256 ? 128u : cap);
-                const uint32_t k = std::max<uint32_t>(std::min<uint32_t>(5, std::max<uint32_t>(1, rem / 32)), (rem + lim - 1) / lim);
-                for (uint32_t i = 0; i < k; i++) plan.push_back(rem * (i + 1) / k - rem * i / k);
-            }
-            if (taper) plan.push_back(taper);
-            plan.push_back(edge);
-        }
-        const uint32_t nBatches = (uint32_t)plan.size();
-        if (nBatches < 2 || nBatches > kMaxPipeBatches) {                    // small input: nothing to overlap
-            s.ctx->batchBlocks = 0;
-            if (len && cudaMemcpyAsync(s.dIn, in + off, len, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
-                rc = fail(FCX_ERR_CUDA, "H2D copy failed");
-            if (rc == FCX_OK)
-                rc = fcx_compress_lz77_device(s.ctx, s.dIn, len, s.dOut, bound, g == 0 ? FCX_WITH_HEADER : 0, n, (uint32_t)nBlocks);
-            if (rc == FCX_OK) rc = fcx_ctx_finish(s.ctx, &bytes[g]);
-            if (rc == FCX_OK && streamOut) {
-                if (bytes[g] > outCap) rc = fail(FCX_ERR_CAPACITY, "output buffer smaller than the compressed result");
-                else if (cudaMemcpyAsync(out, s.dOut, bytes[g], cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
-                         cudaStreamSynchronize(s.stream) != cudaSuccess) rc = fail(FCX_ERR_CUDA, "D2H copy failed");
-            }
-            rcs[g] = rc;
-            if (rc) errs[g] = g_err;
-            return;
-        }
-        cudaError_t e = cudaSuccess;
-        uint64_t o = 0;
-        for (uint32_t k = 0; k < nBatches && e == cudaSuccess; k++) {
-            const uint64_t l = std::min<uint64_t>((uint64_t)plan[k] * kBlockBytes, len - o);
-            e = cudaMemcpyAsync(s.dIn + o, in + off + o, l, cudaMemcpyHostToDevice, s.h2d);
-            if (e == cudaSuccess) e = cudaEventRecord(s.evIn[k], s.h2d);
-            o += l;
-        }
-        if (e != cudaSuccess) { rcs[g] = fail(FCX_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); errs[g] = g_err; return; }
-        BatchHooks hooks;
-        hooks.waitBefore = s.evIn.data(); hooks.recordAfter = s.evOut.data(); hooks.hostCursor = s.hostCursor;
-        hooks.sizes = plan.data(); hooks.nSizes = nBatches;
-        s.ctx->batchBlocks = 0;
-        if (((uintptr_t)s.dIn & 15) || ((uintptr_t)s.dOut & 15)) rc = fail(FCX_ERR_ARG, "device pointers must be 16-byte aligned");
-        if (rc == FCX_OK) rc = run_batches(s.ctx, s.dIn, len, s.dOut, bound, g == 0 ? FCX_WITH_HEADER : 0, n, (uint32_t)nBlocks, &hooks);
-        s.ctx->batchBlocks = 0;
-        if (rc == FCX_OK && streamOut) {
-            uint64_t prev = 0;
-            for (uint32_t k = 0; k < nBatches && rc == FCX_OK; k++) {
-                if (cudaEventSynchronize(s.evOut[k]) != cudaSuccess) { rc = fail(FCX_ERR_CUDA, "batch failed"); break; }
-                const uint64_t cur = s.hostCursor[k];
-                if (cur > outCap || cur > bound) { rc = fail(FCX_ERR_CAPACITY, "output buffer smaller than the compressed result"); break; }
-                if (cur > prev && cudaMemcpyAsync(out + prev, s.dOut + prev, cur - prev, cudaMemcpyDeviceToHost, s.d2h) != cudaSuccess)
-                    rc = fail(FCX_ERR_CUDA, "D2H copy failed");
-                prev = cur;
-            }
-        }
-        uint64_t got = 0;
-        const int frc = fcx_ctx_finish(s.ctx, &got);                         // syncs the kernel stream, reports device-side errors
-        if (rc == FCX_OK) rc = frc;
-        if (rc == FCX_OK && streamOut && cudaStreamSynchronize(s.d2h) != cudaSuccess) rc = fail(FCX_ERR_CUDA, "D2H copy failed");
-        bytes[g] = got;
-        rcs[g] = rc;
-        if (rc) errs[g] = g_err;
-    };
-    if (G == 1) shard(0);
-    else {
-        std::vector<std::thread> th;
-        for (size_t g = 0; g < G; g++) th.emplace_back(shard, g);
-        for (auto &t : th) t.join();
-    }
-    for (size_t g = 0; g < G; g++) if (rcs[g]) return fail(rcs[g], errs[g]);
-    uint64_t total = 0;
-    for (size_t g = 0; g < G; g++) total += bytes[g];
-    if (total > outCap) return fail(FCX_ERR_CAPACITY, "output buffer smaller than the compressed result");
-    if (streamOut) { *outN = total; return FCX_OK; }                     // already copied batch by batch
-    // place the shards: only their byte counts cross devices (host prefix sum)
-    uint64_t at = 0;
-    for (size_t g = 0; g < G; g++) {
-        DevSlot &s = g_slots[devs[g]];
-        CK(cudaSetDevice(devs[g]));
-        CK(cudaMemcpyAsync(out + at, s.dOut, bytes[g], cudaMemcpyDeviceToHost, s.stream));
-        at += bytes[g];
-    }
-    for (size_t g = 0; g < G; g++) { CK(cudaSetDevice(devs[g])); CK(cudaStreamSynchronize(g_slots[devs[g]].stream)); }
-    *outN = total;
-    return FCX_OK;
-}
-
-extern "C" int fcx_compress_block_lz77(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t outCap, uint32_t *outN)
-{
-    if (!in || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");             // mc:2122-2123
-    if (n == 0 || n > kBlockBytes) return fail(FCX_ERR_ARG, "a block holds 1..1048576 bytes (mc:4090)");
-    if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
-    DevSlot &s = g_slots[0];
-    std::lock_guard<std::mutex> lk(s.mu);
-    const uint64_t bound = fcx_compress_bound(n);
-    int rc = slot_prepare(s, 0, n, bound);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(s.dIn, in, n, cudaMemcpyHostToDevice, s.stream));
-    rc = fcx_compress_lz77_device(s.ctx, s.dIn, n, s.dOut, bound, 0, 0, 0);
-    uint64_t bytes = 0;
-    if (rc == FCX_OK) rc = fcx_ctx_finish(s.ctx, &bytes);
-    if (rc) return rc;
-    if (bytes < 4 || bytes - 4 > outCap) return fail(FCX_ERR_CAPACITY, "output buffer smaller than the payload");
-    CK(cudaMemcpy(out, s.dOut + 4, bytes - 4, cudaMemcpyDeviceToHost));             // strip the record's u32 size
-    *outN = (uint32_t)(bytes - 4);
-    return FCX_OK;
-}
-
-// -----------------------------------------------------------------------------------------
-// decompress (device kernels in fcx_decode.cu)
-// -----------------------------------------------------------------------------------------
-static int decode_on_device(int dev, const uint8_t *file, uint64_t nbytes, const std::vector<uint64_t> &recOff,
-                            uint8_t *out, uint64_t outCap, uint64_t *outN)
-{
-    DevSlot &s = g_slots[dev];
-    std::lock_guard<std::mutex> lk(s.mu);
-    const uint32_t nb = (uint32_t)recOff.size();
-    const uint64_t rawCap = (uint64_t)nb * kBlockBytes + 16;       // block b decodes to dOut + b MiB
-    int rc = slot_prepare(s, dev, nbytes + 16, rawCap);
-    if (rc) return rc;
-    fcx_ctx *c = s.ctx;
+    if (!c || !d_file || !recOff || !d_out || !lens) return fail(FCX_ERR_ARG, "null pointer");
+    if (nBlocks == 0) return FCX_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    constexpr uint32_t kBatch = 128;                      // blocks decoded per launch: bounds the scratch
     const size_t per = decode_scratch_per_block();
-    if (s.decScratchCap < per * nb) {
-        if (s.decScratch) cudaFree(s.decScratch);
-        s.decScratch = nullptr; s.decScratchCap = 0;
-        CK(cudaMalloc(&s.decScratch, per * nb + 256));
-        s.decScratchCap = per * nb;
+    if (!c->decScratch) {
+        CK(cudaMalloc(&c->decScratch, per * kBatch + 256));
+        CK(cudaMalloc(&c->decRec, sizeof(uint64_t) * kBatch));
+        CK(cudaMalloc(&c->decLen, sizeof(uint32_t) * kBatch));
     }
-    if (s.decBlocks < nb) {
-        if (s.decRec) cudaFree(s.decRec);
-        if (s.decLen) cudaFree(s.decLen);
-        s.decRec = nullptr; s.decLen = nullptr; s.decBlocks = 0;
-        CK(cudaMalloc(&s.decRec, sizeof(uint64_t) * (nb + 1)));
-        CK(cudaMalloc(&s.decLen, sizeof(uint32_t) * (nb + 1)));
-        s.decBlocks = nb;
+    for (uint32_t b0 = 0; b0 < nBlocks; b0 += kBatch) {
+        const uint32_t nb = std::min(kBatch, nBlocks - b0);
+        // pageable source: the copy returns once the offsets are staged, so the caller's array may change afterwards
+        CK(cudaMemcpyAsync(c->decRec, recOff + b0, sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, st));
+        c->launches += launch_decode(d_file, c->decRec, nb, d_out + (size_t)b0 * kBlockBytes, c->decLen, c->decScratch, per, st);
+        CK(cudaMemcpyAsync(lens + b0, c->decLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaMemcpyAsync(s.dIn, file, nbytes, cudaMemcpyHostToDevice, s.stream));
-    CK(cudaMemsetAsync(s.dIn + nbytes, 0, 16, s.stream));
-    CK(cudaMemcpyAsync(s.decRec, recOff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s.stream));
-    c->launches += launch_decode(s.dIn, s.decRec, nb, s.dOut, s.decLen, s.decScratch, per, s.stream);
-    std::vector<uint32_t> lens(nb);
-    CK(cudaMemcpyAsync(lens.data(), s.decLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    uint64_t total = 0;
-    bool packed = true;                                            // every block but the last is full: one copy
-    for (uint32_t b = 0; b < nb; b++) {
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (uint32_t b = 0; b < nBlocks; b++)
         if (lens[b] == 0xFFFFFFFFu) return fail(FCX_ERR_FORMAT, "corrupt block payload");
-        if (b + 1 < nb && lens[b] != kBlockBytes) packed = false;
-        total += lens[b];
-    }
-    if (total > outCap) return fail(FCX_ERR_CAPACITY, "output buffer too small");
-    if (packed) {
-        if (total) CK(cudaMemcpyAsync(out, s.dOut, total, cudaMemcpyDeviceToHost, s.stream));
-    } else {
-        uint64_t at = 0;
-        for (uint32_t b = 0; b < nb; b++) {
-            if (lens[b]) CK(cudaMemcpyAsync(out + at, s.dOut + (uint64_t)b * kBlockBytes, lens[b], cudaMemcpyDeviceToHost, s.stream));
-            at += lens[b];
-        }
-    }
-    CK(cudaStreamSynchronize(s.stream));
-    *outN = total;
-    return FCX_OK;
-}
-
-extern "C" int fcx_decompress_lz77(const uint8_t *file, uint64_t nbytes, uint8_t *out, uint64_t outCap, uint64_t *outN,
-                                   uint32_t deviceMask)
-{
-    if (!file || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");
-    if (nbytes < 10) return fail(FCX_ERR_FORMAT, "shorter than the 10-byte header");               // mc:4139-4144
-    if (memcmp(file, "FCX", 3) != 0) return fail(FCX_ERR_FORMAT, "not an FCX container");          // mc:4146-4152
-    if (file[3] != '7') return fail(FCX_ERR_UNSUPPORTED, "FCX8 (lz78) containers are not on this path");
-    if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
-    uint16_t nb16; memcpy(&nb16, file + 8, 2);
-    std::vector<uint64_t> rec;
-    uint64_t pos = 10;
-    for (uint32_t b = 0; b < nb16; b++) {                                                          // mc:4162-4174
-        if (pos + 4 > nbytes) return fail(FCX_ERR_FORMAT, "truncated record header");
-        uint32_t sz; memcpy(&sz, file + pos, 4);
-        if (pos + 4 + sz > nbytes) return fail(FCX_ERR_FORMAT, "truncated record");
-        rec.push_back(pos);
-        pos += 4 + sz;
-    }
-    if (rec.empty()) { *outN = 0; return FCX_OK; }
-    int dev = 0;
-    for (int g = 0; g < 32; g++) if (deviceMask & (1u << g)) { dev = g; break; }
-    if (dev >= fcx_device_count()) return fail(FCX_ERR_ARG, "device_mask selects no visible device");
-    return decode_on_device(dev, file, nbytes, rec, out, outCap, outN);
-}
-
-extern "C" int fcx_decompress_block_lz77(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t outCap,
-                                         uint32_t *outN)
-{
-    if (!payload || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");                      // mc:2257-2258
-    if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
-    std::vector<uint8_t> rec(4 + (size_t)nbytes);
-    memcpy(rec.data(), &nbytes, 4);
-    memcpy(rec.data() + 4, payload, nbytes);
-    std::vector<uint64_t> off(1, 0);
-    uint64_t got = 0;
-    int rc = decode_on_device(0, rec.data(), rec.size(), off, out, outCap, &got);
-    if (rc) return rc;
-    *outN = (uint32_t)got;
     return FCX_OK;
 }
 

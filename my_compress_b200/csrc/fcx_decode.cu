@@ -452,6 +452,8 @@ k_decode(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff, 
     }
 }
 
+void decode_init() {}
+
 int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out,
                   uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st)
 {

@@ -11,6 +11,7 @@
 namespace fcx {
 
 constexpr uint32_t kBlockBytes = 1u << 20;
+constexpr uint32_t kMaxBatchBlocks = 1024;      // blocks per device batch (stream ids b*4+k < 4096, 32-bit arena offsets)
 constexpr int kWindow = 2047;
 constexpr int kMaxLen = 257;   // min(258, n-i) - 1
 constexpr int kMinLen = 3;

@@ -279,12 +279,6 @@ k_chunk_bits(Ws ws)
 
 // chunk bit offsets inside each stream (<= 128 chunks per stream: one thread per stream), and the
 // 16-byte descriptor k_encode_w reads per chunk (runs after k_block_layout: needs segBitBase)
-#ifndef FCX_ENC_STAGE_WORDS
-#define FCX_ENC_STAGE_WORDS 3064      // tests build a variant with a tiny stage to exercise the dense path
-#endif
-constexpr uint32_t kEncStageWords = FCX_ENC_STAGE_WORDS;
-constexpr uint32_t kEncStageBits = kEncStageWords * 32;
-
 // chunk descriptor: x = byte offset of the chunk inside its stream arena, z:w = absolute bit
 // position of its first code word bit in the container, y = the fields below
 constexpr uint32_t CD_CNT_MASK = 0x3FFFu;     // symbols in the chunk (<= 8192)
@@ -292,9 +286,11 @@ constexpr int CD_K_SHIFT = 14;                // stream kind 0..3
 constexpr int CD_GROUP_SHIFT = 16;            // symbols merged per 32-bit insert: 4 / 3 / 2 / 1; 5 = fixed 8-bit codes (k_encode_w only)
 constexpr int CD_SKIP_SHIFT = 19;             // not the fast kernel's: single-symbol stream (no bits) or a slow chunk
 constexpr int CD_SEG_SHIFT = 20;              // stream id b*4+k (< 4096)
+static_assert(4ull * kMaxBatchBlocks <= (1ull << (32 - CD_SEG_SHIFT)), "stream id of the last block of a batch fits the descriptor");
+static_assert((unsigned long long)kMaxBatchBlocks * kSegStride1 < (1ull << 32), "stream arena offsets are 32-bit");
 
 __global__ void __launch_bounds__(256)
-k_seg_scan(Ws ws, uint32_t nSeg, uint32_t stageBits, uint32_t fixedPath)
+k_seg_scan(Ws ws, uint32_t nSeg)
 {
     // one warp per stream: 32 chunks per trip, warp prefix sum of their bit lengths
     const int lane = threadIdx.x & 31;
@@ -305,7 +301,7 @@ k_seg_scan(Ws ws, uint32_t nSeg, uint32_t stageBits, uint32_t fixedPath)
     const uint32_t maxlen = si[SI_MAXLEN] & 0xFFu, minlen = si[SI_MAXLEN] >> 8;
     const bool longCodes = maxlen > 24;                      // fast path keeps a code in 24 bits (GROUP 1) or merges 2..4 into 32
     // 5: every code is exactly 8 bits (flat histogram over all 256 bytes: incompressible input), a byte translation
-    const uint32_t group = (fixedPath && maxlen == 8 && minlen == 8) ? 5u : maxlen <= 8 ? 4u : maxlen <= 10 ? 3u : maxlen <= 16 ? 2u : 1u;
+    const uint32_t group = (maxlen == 8 && minlen == 8) ? 5u : maxlen <= 8 ? 4u : maxlen <= 10 ? 3u : maxlen <= 16 ? 2u : 1u;
     const uint32_t b = s >> 2, k = s & 3;
     const unsigned long long bitBase = ws.segBitBase[s];
     const uint32_t arena = b * ws.strmStride[k];
@@ -323,7 +319,7 @@ k_seg_scan(Ws ws, uint32_t nSeg, uint32_t stageBits, uint32_t fixedPath)
         const uint32_t off = running + inc - bits;
         if (have) {
             ws.chunkBitOff[first + c] = off;
-            const bool sl = W != 0 && (longCodes || bits > stageBits);   // does not fit the CTA-wide stage at any alignment (k_encode only)
+            const bool sl = W != 0 && longCodes;                          // k_encode_slow's
             ws.chunkSlow[first + c] = sl ? 1 : 0;
             slow += sl ? 1u : 0u;
             const uint32_t cnt = min((uint32_t)kChunkSyms, S - c * kChunkSyms);
@@ -504,34 +500,27 @@ k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
 // =========================================================================================
 // encode: the HBM-bound kernel (algorithmic bytes = S_in + S_out)
 // =========================================================================================
-// Two generations live here.  k_encode (CTA per chunk, TMA prefetch, three barriers per chunk) is the earlier
-// one, kept selectable with FCX_ENCODE=cta for A/B runs; k_encode_w further down (warp per sub-chunk, no
-// barriers in the chunk loop) is what launch_huff_stage runs.  k_encode_slow takes the streams whose codes are
-// longer than 24 bits for both.
-// One CTA encodes a contiguous range of 8192-symbol chunks.  Each thread owns a run of 32
-// consecutive symbols (two 16-byte loads).  Pass 1 looks every symbol up once in a table that
-// is replicated 32x in shared memory (tab[sym*32 + lane]: bank == lane, conflict-free) and
-// keeps the 32 entries in registers; a CTA scan of the run lengths gives every run its bit
-// position.  Pass 2 packs from registers: codes are first merged GROUP at a time in a 32-bit
-// word (4 symbols when no code is longer than 8 bits, 2 up to 16, 1 up to 24), then inserted
-// into a 64-bit accumulator whose low word is flushed to a shared staging buffer.  A run is
-// >= 32 bits, so a staging word has at most two writers: the tail of run t travels by shuffle
-// into the first word of run t+1 -- no atomics inside the CTA.  The staged words go out as
-// coalesced 4-byte stores; only the first/last word of a chunk (shared with the neighbouring
-// chunk or with header bytes) is merged with atomicOr on the pre-zeroed container.
+// k_encode_w (warp per sub-chunk, no barriers in the chunk loop) is the encoder; k_encode_slow takes the
+// rare streams whose codes are longer than 24 bits.  Common ground: a thread owns a run of 32 consecutive
+// symbols (two 16-byte loads), looks every symbol up once in a shared-memory table replicated per lane
+// (conflict-free), a scan of the run lengths gives every run its bit position, and the codes are packed
+// from registers through a 64-bit accumulator whose low word is flushed to a shared staging buffer.  A run
+// is >= 32 bits, so a staging word has at most two writers: the tail of run t travels by shuffle into the
+// first word of run t+1 -- no atomics inside the stage.  The staged words go out coalesced; only the
+// first/last word of a (sub-)chunk (shared with its neighbour or with header bytes) is merged with atomicOr
+// on the pre-zeroed container.
 constexpr int ENC_THREADS = 256;
 constexpr int ENC_RUN = kChunkSyms / ENC_THREADS;     // 32 symbols per thread
 static_assert(ENC_RUN == 32, "run length is baked into the carry logic (>= 32 bits per run)");
-constexpr int ENC_STAGE_WORDS = (int)kEncStageWords;                 // 16 bits per symbol on average; denser chunks take the slow path
+constexpr int ENC_STAGE_WORDS = 3064;                 // k_encode_slow's CTA-wide stage; denser chunks go straight to the container
+constexpr int ENC_DESC_BATCH = 64;
 
 struct EncSmem {
-    uint32_t tab[256 * 32];            // fast path: code | len<<24; generic path: code | 1<<len
+    uint32_t tab[256 * 32];            // code | 1<<len, one copy per lane
     alignas(16) uint32_t stage[ENC_STAGE_WORDS + 8];
     uint32_t warpBits[8];
     uint32_t warpTail[8];
 };
-
-size_t encode_smem_bytes() { return sizeof(EncSmem); }
 
 __device__ __forceinline__ uint32_t enc_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t enc_lds(uint32_t a)
@@ -544,28 +533,11 @@ __device__ __forceinline__ void enc_sts(uint32_t a, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 }
-
-// pack 32 table entries (code | len<<24) starting at staging bit p0; returns tail bits / word index
-template <int GROUP>
-__device__ __forceinline__ void enc_pack_fast(const uint32_t (&ent)[32], uint32_t p0, uint32_t stageA,
-                                              uint32_t &tail, uint32_t &tailIdx)
+__device__ __forceinline__ uint2 enc_lds64(uint32_t a)
 {
-    uint32_t lo = 0, hi = 0, accBits = p0 & 31, w = stageA + 4 * (p0 >> 5);
-#pragma unroll
-    for (int j = 0; j < 32; j += GROUP) {
-        uint32_t g = 0, gl = 0;
-#pragma unroll
-        for (int k = 0; k < GROUP; k++) {
-            const uint32_t e = ent[j + k];
-            g |= (e & 0xFFFFFFu) << gl;
-            gl += e >> 24;
-        }
-        lo |= g << accBits;
-        hi |= __funnelshift_l(g, 0u, accBits);     // bits of g that spill past bit 31 (0 when accBits == 0)
-        accBits += gl;
-        if (accBits >= 32) { enc_sts(w, lo); w += 4; lo = hi; hi = 0; accBits -= 32; }
-    }
-    tail = lo; tailIdx = (w - stageA) >> 2;
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
 }
 
 // generic path, sentinel entries (code | 1<<len, len <= 31): one 64-bit insert per symbol
@@ -585,253 +557,15 @@ __device__ __forceinline__ void enc_pack_generic(const uint32_t (&ent)[32], uint
     tail = (uint32_t)acc; tailIdx = (w - stageA) >> 2;
 }
 
-// ---- fast kernel -------------------------------------------------------------------------
-// Table entries are {code, len} pairs read with one 64-bit shared load (no extraction ops),
-// replicated 16x: lanes l and l+16 share a copy but sit in different half-warp phases of a
-// 64-bit access, so the look-ups stay conflict-free in 32 KB.  Codes are merged GROUP at a time
-// while they are looked up (4 when no code exceeds 8 bits, 3 up to 10, 2 up to 16, 1 up to 24),
-// so the pack pass inserts 8 / 11 / 16 / 32 words per run.
-//
-// Nothing in the chunk loop waits on global memory: the CTA copies the 16-byte descriptors of its
-// next 64 chunks to shared memory in one go, and the symbols of the NEXT chunk arrive by one TMA
-// bulk copy (cp.async.bulk + mbarrier, issued by thread 0 right after the scan barrier, when every
-// thread has consumed the buffer) while the current chunk is packed and copied out.  Only a change
-// of stream reloads the code table.
-//
-// Stage addressing is swizzled at 16-byte granularity (unit u lives at u ^ ((u >> 3) & 7)): runs
-// of equal length (uniform data: 8 words per run) would otherwise put every lane of a store on
-// the same four banks.  Whole units stay intact, so the copy-out still moves 128 bits at a time.
-constexpr int ENC_DESC_BATCH = 64;
-static_assert((ENC_STAGE_WORDS + 8) % 32 == 0, "the stage swizzle permutes inside aligned 32-word groups");
-struct EncFastSmem {
-    alignas(1024) uint32_t stage[ENC_STAGE_WORDS + 8];
-    alignas(16) unsigned long long tab[256 * 16];      // tab[sym*16 + (lane & 15)] = code | (u64)len << 32
-    alignas(16) uint8_t sym[kChunkSyms];               // the chunk's symbols as they lie in the stream
-    alignas(16) uint4 desc[ENC_DESC_BATCH];
-    alignas(8) unsigned long long mbar;                // completion barrier of the bulk copy into sym
-    uint32_t warpBits[8];
-    uint32_t warpTail[8];
-};
-
-__device__ __forceinline__ uint2 enc_lds64(uint32_t a)
-{
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
-}
-
-// byte offset of stage word k / index of stage unit v after the swizzle
+// Optional stage swizzle at 16-byte granularity (unit u lives at u ^ ((u >> 3) & 7)): runs of equal length
+// would otherwise put every lane of a store on the same four banks.  Whole units stay intact, so the
+// copy-out still moves 128 bits at a time.  (See FCX_ENCW_SWIZZLE below.)
 __device__ __forceinline__ uint32_t enc_swz_byte(uint32_t byteOff) { return byteOff ^ ((byteOff >> 3) & 0x70u); }
 __device__ __forceinline__ uint32_t enc_swz_word(uint32_t k) { return k ^ (((k >> 5) & 7u) << 2); }
 __device__ __forceinline__ uint32_t enc_swz_unit(uint32_t v) { return v ^ ((v >> 3) & 7u); }
 
-// one bulk copy global -> sym, completion signalled on mbar (one elected thread calls this)
-__device__ __forceinline__ void enc_bulk_fetch(uint32_t symA, uint32_t mbarA, const uint8_t *src, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbarA), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(symA), "l"(src), "r"(bytes), "r"(mbarA) : "memory");
-}
-__device__ __forceinline__ void enc_bulk_wait(uint32_t mbarA, uint32_t phase)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "ENC_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra ENC_WAIT_%=;\n"
-        "}\n" :: "r"(mbarA), "r"(phase) : "memory");
-}
-
-template <int GROUP>
-__device__ __forceinline__ uint32_t enc_fast_chunk(EncFastSmem &sm, uint32_t *__restrict__ out32, uint32_t cnt,
-                                                   unsigned long long gb0, uint32_t tabLane, uint32_t stageA, uint32_t symA,
-                                                   uint32_t mbarA, uint32_t phase, const uint8_t *nextSrc, uint32_t nextRuns)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nRuns = cnt / ENC_RUN;
-    const bool active = (uint32_t)tid < nRuns;
-    constexpr int NG = (32 + GROUP - 1) / GROUP;
-    // GROUP 4 / 3 / 2: g = merged codes, gl = their total length.  GROUP 1 (codes up to 24 bits): one
-    // register per symbol, code | len << 24, and gl is not used.
-    uint32_t g[NG], gl[GROUP == 1 ? 1 : NG];
-    uint32_t myBits = 0;
-    if (nRuns) enc_bulk_wait(mbarA, phase);
-    if (active) {
-        uint4 a, d;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(symA + tid * 32));
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(symA + tid * 32 + 16));
-        const uint32_t sy[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int q = 0; q < NG; q++) {
-            uint32_t acc = 0, len = 0;
-#pragma unroll
-            for (int k = 0; k < GROUP; k++) {
-                const int j = q * GROUP + k;
-                if (j < 32) {
-                    const uint32_t sym = __byte_perm(sy[j >> 2], 0u, 0x4440u + (j & 3));
-                    const uint2 e = enc_lds64(tabLane + (sym << 7));
-                    acc |= e.x << len;
-                    len += e.y;
-                }
-            }
-            if (GROUP == 1) g[q] = acc | (len << 24);
-            else { g[q] = acc; gl[q] = len; }
-            myBits += len;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < NG; q++) g[q] = 0;
-    }
-    // ---- CTA scan of the run lengths --------------------------------------------------------
-    uint32_t inc = myBits;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) sm.warpBits[warp] = inc;
-    __syncthreads();
-    // every thread has consumed its symbols (myBits depends on all of them): refill the buffer
-    if (tid == 0 && nextRuns) enc_bulk_fetch(symA, mbarA, nextSrc, nextRuns * ENC_RUN);
-    uint32_t wbase = 0, fullBits = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) { const uint32_t v = sm.warpBits[w]; if (w < warp) wbase += v; fullBits += v; }
-    // stage word k holds container word wBase + k (wBase a multiple of 4: 16-byte units line up)
-    const uint32_t r0 = (uint32_t)(gb0 & 127);
-    const unsigned long long wBase = (gb0 >> 5) & ~3ull;
-    const uint32_t p0 = r0 + wbase + inc - myBits;
-    // ---- pack: insert the groups, flush the low word of the 64-bit accumulator -----------------
-    uint32_t tail = 0, tailIdx = 0;
-    if (active) {
-        uint32_t lo = 0, accBits = p0 & 31, w = 4 * (p0 >> 5);
-#pragma unroll
-        for (int q = 0; q < NG; q++) {
-            const uint32_t bitsq = GROUP == 1 ? (g[q] & 0xFFFFFFu) : g[q];
-            const uint32_t lenq = GROUP == 1 ? (g[q] >> 24) : gl[q];
-            lo |= bitsq << accBits;
-            const uint32_t hi = __funnelshift_l(bitsq, 0u, accBits);     // bits that spill past bit 31 (0 when accBits == 0)
-            accBits += lenq;
-            if (accBits >= 32) { enc_sts(stageA + enc_swz_byte(w), lo); w += 4; lo = hi; }
-            accBits &= 31;
-        }
-        tail = lo; tailIdx = w >> 2;
-    }
-    // the tail of run t-1 lives in the low bits of the head word of run t
-    const uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
-    if (lane == 31) sm.warpTail[warp] = tail;
-    const uint32_t headIdx = enc_swz_word(p0 >> 5);
-    if (active) {
-        if (lane > 0) sm.stage[headIdx] |= prevTail;                            // own word, own earlier store
-        if ((uint32_t)tid == nRuns - 1) sm.stage[enc_swz_word(tailIdx)] = tail; // nobody follows: park the tail
-    }
-    __syncthreads();
-    if (active && lane == 0 && warp > 0) sm.stage[headIdx] |= sm.warpTail[warp - 1];
-    __syncthreads();
-    // ---- copy out: whole 16-byte units as 128-bit stores, shared edge words by atomicOr --------
-    const uint32_t first = r0 >> 5, fbit = r0 & 31;
-    const uint32_t endBit = r0 + fullBits, last = endBit >> 5, rem = endBit & 31;
-    uint32_t *dst = out32 + wBase;
-    const uint32_t vBeg = (first + (fbit ? 1u : 0u) + 3u) >> 2, vEnd = last >> 2;
-    if (vBeg < vEnd) {
-        for (uint32_t v = vBeg + tid; v < vEnd; v += ENC_THREADS)
-            reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(sm.stage)[enc_swz_unit(v)];
-        if (tid < 8) {                                               // scalar edges
-            const uint32_t k = tid < 4 ? first + tid : 4 * vEnd + (tid - 4);
-            const bool inHead = tid < 4 && k < 4 * vBeg, inTail = tid >= 4 && k < last;
-            if (inHead || inTail) {
-                const uint32_t v = sm.stage[enc_swz_word(k)];
-                if (k == first && fbit) atomicOr(&dst[k], v); else dst[k] = v;
-            }
-        }
-    } else {
-        for (uint32_t k = first + tid; k < last; k += ENC_THREADS) {
-            const uint32_t v = sm.stage[enc_swz_word(k)];
-            if (k == first && fbit) atomicOr(&dst[k], v); else dst[k] = v;
-        }
-    }
-    if (tid == 0 && rem && nRuns) atomicOr(&dst[last], sm.stage[enc_swz_word(last)]);
-    return fullBits;
-}
-
-__global__ void __launch_bounds__(ENC_THREADS, 4)
-k_encode(Ws ws, uint32_t *__restrict__ out32)
-{
-    extern __shared__ __align__(1024) unsigned char enc_smem_raw[];
-    EncFastSmem &sm = *reinterpret_cast<EncFastSmem *>(enc_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (ws.totals[TOT_ERR]) return;                     // capacity / internal error: write nothing
-    const uint32_t nChunks = ws.totals[TOT_CHUNKS];
-    const uint32_t cBeg = (uint32_t)((unsigned long long)nChunks * blockIdx.x / gridDim.x);
-    const uint32_t cEnd = (uint32_t)((unsigned long long)nChunks * (blockIdx.x + 1) / gridDim.x);
-    const uint32_t tabLane = enc_smem_addr(sm.tab) + 8 * (lane & 15), stageA = enc_smem_addr(sm.stage);
-    const uint32_t symA = enc_smem_addr(sm.sym), mbarA = enc_smem_addr(&sm.mbar);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbarA) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    uint32_t curSeg = 0xFFFFFFFFu, pfChunk = 0xFFFFFFFFu, phase = 0;
-    for (uint32_t base = cBeg; base < cEnd; base += ENC_DESC_BATCH) {
-        const uint32_t nb = min((uint32_t)ENC_DESC_BATCH, cEnd - base);
-        __syncthreads();                                // everyone is done with the previous batch of descriptors
-        if ((uint32_t)tid < nb) sm.desc[tid] = ws.chunkDesc[base + tid];
-        __syncthreads();
-        uint32_t i = 0;
-        while (i < nb && ((sm.desc[i].y >> CD_SKIP_SHIFT) & 1u)) i++;
-        while (i < nb) {
-            const uint4 d = sm.desc[i];
-            uint32_t j = i + 1;                         // the next chunk that is ours
-            while (j < nb && ((sm.desc[j].y >> CD_SKIP_SHIFT) & 1u)) j++;
-            const uint32_t cnt = d.y & CD_CNT_MASK, group = (d.y >> CD_GROUP_SHIFT) & 7u, s = d.y >> CD_SEG_SHIFT;
-            const uint8_t *src = ws.strm[(d.y >> CD_K_SHIFT) & 3u] + d.x;
-            const unsigned long long gb0 = (unsigned long long)d.z | ((unsigned long long)d.w << 32);
-            // first chunk of a batch: nobody fetched it ahead (all threads are past the previous scan barrier)
-            if (pfChunk != base + i && tid == 0 && cnt >= ENC_RUN) enc_bulk_fetch(symA, mbarA, src, (cnt / ENC_RUN) * ENC_RUN);
-            if (s != curSeg) {
-                const uint32_t e = ws.segTab[(size_t)s * 256 + tid];         // ENC_THREADS == 256 symbols; code | 1<<len
-                const uint32_t len = e ? (uint32_t)(31 - __clz(e)) : 0u;
-                const unsigned long long ent = (unsigned long long)(e ? (e ^ (1u << len)) : 0u) | ((unsigned long long)len << 32);
-                __syncthreads();                        // ragged-tail reader of the previous stream is done with the table
-#pragma unroll 4
-                for (int c = 0; c < 16; c++) sm.tab[tid * 16 + ((c + lane) & 15)] = ent;
-                curSeg = s;
-                __syncthreads();
-            }
-            const uint8_t *nextSrc = nullptr;
-            uint32_t nextRuns = 0;
-            if (j < nb) {
-                const uint4 dn = sm.desc[j];
-                nextSrc = ws.strm[(dn.y >> CD_K_SHIFT) & 3u] + dn.x;
-                nextRuns = (dn.y & CD_CNT_MASK) / ENC_RUN;
-                pfChunk = base + j;
-            }
-            const uint32_t fullBits =
-                group == 4   ? enc_fast_chunk<4>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns)
-                : group == 3 ? enc_fast_chunk<3>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns)
-                : group == 2 ? enc_fast_chunk<2>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns)
-                             : enc_fast_chunk<1>(sm, out32, cnt, gb0, tabLane, stageA, symA, mbarA, phase, nextSrc, nextRuns);
-            if (cnt >= ENC_RUN) phase ^= 1u;            // one completed bulk copy per chunk that has a full run
-            // ---- ragged end of the stream (< 32 symbols): serial append ---------------------------
-            const uint32_t nRuns = cnt / ENC_RUN;
-            if (tid == 0 && cnt > nRuns * ENC_RUN) {
-                unsigned long long bp = gb0 + fullBits;
-                for (uint32_t t = nRuns * ENC_RUN; t < cnt; t++) {
-                    const unsigned long long e = sm.tab[(uint32_t)src[t] * 16];
-                    const unsigned long long v = (e & 0xFFFFFFFFull) << (bp & 31);
-                    if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
-                    if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
-                    bp += (uint32_t)(e >> 32);
-                }
-            }
-            // no barrier here: the scan barrier of the next chunk orders this copy-out before the next
-            // pack, and warpBits / warpTail are rewritten only after barriers every thread has passed
-            i = j;
-        }
-    }
-}
-
 // ---- warp-autonomous fast kernel ------------------------------------------------------------
-// Same tables, groups and stage format as k_encode, but the unit of work is a WARP: warp w of the
+// The unit of work is a WARP: warp w of the
 // CTA owns sub-chunk w (1024 symbols, 32 per lane) of every chunk in the CTA's range, with a
 // private 2 KB stage.  There is no CTA barrier in the chunk loop (only when the stream -- the code
 // table -- changes and once per 64 descriptors): the bit position of a sub-chunk is the chunk's
@@ -859,7 +593,7 @@ constexpr uint32_t EW_STAGE_BITS = (uint32_t)EW_STAGE_WORDS * 32u - 32u;
 constexpr uint32_t EW_PREF_SHIFT = 18;                 // low 18 bits: bit count of one sub-chunk
 static_assert((uint32_t)kChunkSyms * 24u < (1u << EW_PREF_SHIFT), "a chunk's bit count fits the prefix field");
 
-// Stage swizzle of k_encode_w (same permutation as k_encode's).  Off by default: the streams whose runs all
+// Stage swizzle of k_encode_w.  Off by default: the streams whose runs all
 // have the same length -- the case the swizzle exists for -- are the fixed 8-bit ones, and those no longer
 // touch the stage; without it every flush is three instructions shorter.
 #ifndef FCX_ENCW_SWIZZLE
@@ -1229,17 +963,14 @@ k_encode_slow(Ws ws, uint32_t *__restrict__ out32)
     const uint32_t cBeg = blockIdx.x * per, cEnd = min(nChunks, cBeg + per);
     const uint32_t tabLane = enc_smem_addr(sm.tab) + 4 * lane, stageA = enc_smem_addr(sm.stage);
     uint32_t curSeg = 0xFFFFFFFFu;
-    uint32_t mode = 0;                                  // 4/2/1: fast path group size, 0: generic
     for (uint32_t chunk = cBeg; chunk < cEnd; chunk++) {
         const uint32_t s = ws.chunkSeg[chunk];
         const uint32_t *si = ws.segInfo + (size_t)s * SI_WORDS;
         if (!ws.chunkSlow[chunk]) continue;             // the fast kernel's
         if (s != curSeg) {
-            mode = 0;                                   // always the generic representation here
             __syncthreads();
             uint32_t e = ws.segTab[(size_t)s * 256 + tid];      // ENC_THREADS == 256 symbols
-            if (mode && e) { const uint32_t len = (uint32_t)(31 - __clz(e)); e = (e ^ (1u << len)) | (len << 24); }
-            if (!mode && !e) e = 1;                              // absent symbol: zero-length sentinel (never looked up)
+            if (!e) e = 1;                              // absent symbol: zero-length sentinel (never looked up)
 #pragma unroll 8
             for (int c = 0; c < 32; c++) sm.tab[tid * 32 + ((c + lane) & 31)] = e;
             curSeg = s;
@@ -1271,16 +1002,11 @@ k_encode_slow(Ws ws, uint32_t *__restrict__ out32)
                 const uint32_t sym = (sy[j >> 2] >> ((j & 3) * 8)) & 0xFF;
                 ent[j] = enc_lds(tabLane + sym * 128);
             }
-            if (mode) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) myBits += ent[j] >> 24;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; j++) myBits += (uint32_t)(31 - __clz(ent[j]));
-            }
+            for (int j = 0; j < 32; j++) myBits += (uint32_t)(31 - __clz(ent[j]));
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++) ent[j] = mode ? 0u : 1u;
+            for (int j = 0; j < 32; j++) ent[j] = 1u;
         }
         uint32_t inc = myBits;
 #pragma unroll
@@ -1299,10 +1025,7 @@ k_encode_slow(Ws ws, uint32_t *__restrict__ out32)
             // ---- pass 2: pack into the stage; head word = first flushed word of the run --------
             uint32_t tail = 0, tailIdx = 0;
             if (active) {
-                if (mode == 4) enc_pack_fast<4>(ent, p0, stageA, tail, tailIdx);
-                else if (mode == 2) enc_pack_fast<2>(ent, p0, stageA, tail, tailIdx);
-                else if (mode == 1) enc_pack_fast<1>(ent, p0, stageA, tail, tailIdx);
-                else enc_pack_generic(ent, p0, stageA, tail, tailIdx);
+                enc_pack_generic(ent, p0, stageA, tail, tailIdx);
             }
             // the tail of run t-1 lives in the low bits of the head word of run t
             const uint32_t prevTail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
@@ -1345,8 +1068,8 @@ k_encode_slow(Ws ws, uint32_t *__restrict__ out32)
                 uint32_t e = 0;
 #pragma unroll
                 for (int q = 0; q < 32; q++) if (q == j) e = ent[q];
-                const uint32_t len = mode ? (e >> 24) : (uint32_t)(31 - __clz(e));
-                const uint32_t code = mode ? (e & 0xFFFFFFu) : (e ^ (1u << len));
+                const uint32_t len = (uint32_t)(31 - __clz(e));
+                const uint32_t code = e ^ (1u << len);
                 const unsigned long long v = (unsigned long long)code << (bp & 31);
                 if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
                 if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
@@ -1358,8 +1081,8 @@ k_encode_slow(Ws ws, uint32_t *__restrict__ out32)
             unsigned long long bp = gb0 + fullBits;
             for (uint32_t i = nRuns * ENC_RUN; i < cnt; i++) {
                 const uint32_t e = sm.tab[(uint32_t)src[i] * 32];
-                const uint32_t len = mode ? (e >> 24) : (uint32_t)(31 - __clz(e));
-                const uint32_t code = mode ? (e & 0xFFFFFFu) : (e ^ (1u << len));
+                const uint32_t len = (uint32_t)(31 - __clz(e));
+                const uint32_t code = e ^ (1u << len);
                 const unsigned long long v = (unsigned long long)code << (bp & 31);
                 if ((uint32_t)v) atomicOr(&out32[bp >> 5], (uint32_t)v);
                 if ((uint32_t)(v >> 32)) atomicOr(&out32[(bp >> 5) + 1], (uint32_t)(v >> 32));
@@ -1420,14 +1143,8 @@ k_headers(Ws ws, uint8_t *__restrict__ out, uint32_t nBlocks, uint32_t withHeade
 // =========================================================================================
 // launches
 // =========================================================================================
-// FCX_ENCODE=cta selects the CTA-per-chunk kernel (k_encode); the default is the warp-autonomous k_encode_w.
-static int g_encCta = 0;
-
 void huff_init()
 {
-    const char *e = getenv("FCX_ENCODE");
-    g_encCta = e && strcmp(e, "cta") == 0;
-    cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncFastSmem));
     cudaFuncSetAttribute(k_encode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncWSmem));
 }
 
@@ -1447,13 +1164,12 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     if (mark) mark(markArg, 4);
     k_chunk_bits<<<numSM * 4, 256, 0, st>>>(ws); launches++;
     k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, withHeader, outCap); launches++;
-    // k_encode_w writes a sub-chunk that is too dense for its stage itself; k_encode leaves such chunks to k_encode_slow
-    k_seg_scan<<<(nSeg + 7) / 8, 256, 0, st>>>(ws, nSeg, g_encCta ? kEncStageBits - 128 : 0xFFFFFFFFu, g_encCta ? 0u : 1u); launches++;
+    // k_encode_w writes a sub-chunk that is too dense for its stage itself; only long-code streams go to k_encode_slow
+    k_seg_scan<<<(nSeg + 7) / 8, 256, 0, st>>>(ws, nSeg); launches++;
     const uint32_t encGrid = (uint32_t)std::min(numSM * EW_CTAS, (int)kMaxEncCtas);
-    if (!g_encCta) { k_enc_split<<<1, 1024, 0, st>>>(ws, nSeg, encGrid); launches++; }
+    k_enc_split<<<1, 1024, 0, st>>>(ws, nSeg, encGrid); launches++;
     if (mark) mark(markArg, 5);
-    if (g_encCta) k_encode<<<numSM * 4, ENC_THREADS, sizeof(EncFastSmem), st>>>(ws, reinterpret_cast<uint32_t *>(out));
-    else k_encode_w<<<encGrid, EW_THREADS, sizeof(EncWSmem), st>>>(ws, reinterpret_cast<uint32_t *>(out));
+    k_encode_w<<<encGrid, EW_THREADS, sizeof(EncWSmem), st>>>(ws, reinterpret_cast<uint32_t *>(out));
     launches++;
     if (mark) mark(markArg, 6);
     k_encode_slow<<<numSM * 2, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;

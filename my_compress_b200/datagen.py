@@ -22,11 +22,15 @@ def _rng(family_id, seed, block):
 
 
 def randm_block(n, seed=0, block=0):
-    """Low bytes of a Fisher-Yates permutation of [0,n) -- what RandM()
-    (随机数的生成.cpp:26-42) yields when each int is stored as one byte: an exactly
-    flat histogram when n is a multiple of 256."""
-    perm = _rng(1, seed, block).permutation(n)
-    return (perm & 0xFF).astype(np.uint8)
+    """Low bytes of the permutation RandM() of the reference's generator program produces
+    (随机数的生成.cpp:26-42: Fisher-Yates driven by libc rand(), time() pinned to the seed), restated in
+    ``fcx_datagen_randm`` (csrc/fcx_api.cu; host code, runs without a GPU): an exactly flat histogram
+    when n is a multiple of 256."""
+    from . import api
+
+    if n == 0:
+        return np.zeros(0, np.uint8)
+    return api.datagen_randm(int(n), (int(seed) * 1000003 + int(block)) & 0x7FFFFFFF)
 
 
 def uniform_block(n, seed=0, block=0):
@@ -89,11 +93,14 @@ FAMILIES = {
     "periodic": periodic_block,
 }
 MIXED_ORDER = ("uniform", "zipf", "phrases")
+PHRASES_VARIANT_BLOCK = 511      # one block of a single repeated byte (l = 257 chain, p = 2047 ties)
 
 
 def block_family(family, block):
     if family == "mixed":
         return MIXED_ORDER[block % 3]
+    if family == "phrases+run":                         # config 3 as the survey words it
+        return "byterun" if block == PHRASES_VARIANT_BLOCK else "phrases"
     return family
 
 
@@ -101,9 +108,10 @@ def gen_block(family, n, seed=0, block=0):
     return FAMILIES[block_family(family, block)](n, seed, block)
 
 
-def gen(family, nbytes, seed=0, first_block=0):
-    """``nbytes`` of corpus ``family`` starting at 1 MiB block ``first_block``."""
-    out = np.empty(nbytes, np.uint8)
+def gen(family, nbytes, seed=0, first_block=0, out=None):
+    """``nbytes`` of corpus ``family`` starting at 1 MiB block ``first_block`` (into ``out`` when given)."""
+    if out is None:
+        out = np.empty(nbytes, np.uint8)
     off = 0
     b = first_block
     while off < nbytes:
@@ -118,7 +126,7 @@ CONFIGS = {
     # name -> (family, bytes)   BASELINE.json configs[0..4]
     "randm-1MiB": ("randm", 1 << 20),
     "zipf-64MiB": ("zipf", 64 << 20),
-    "phrases-1GiB": ("phrases", 1 << 30),
+    "phrases-1GiB": ("phrases+run", 1 << 30),
     "mixed-8GiB": ("mixed", 8 << 30),
     "uniform-1GiB": ("uniform", 1 << 30),
 }

@@ -53,6 +53,15 @@ def test_argument_errors(L):
     assert L.fcx_decompress_lz77(fcx8.ctypes.data, len(fcx8), out.ctypes.data, 64, C.byref(n), 1) == -6
 
 
+def test_context_batch_limit(L):
+    # stream ids in the chunk descriptors and 32-bit arena offsets cap a device batch at 1024 blocks:
+    # larger contexts are refused up front instead of corrupting the container
+    ctx = C.c_void_p(None)
+    assert L.fcx_ctx_create(C.byref(ctx), 0, 1025) == -1
+    assert L.fcx_ctx_create(C.byref(ctx), 0, 0) == -1
+    assert b"1..1024" in L.fcx_last_error()
+
+
 def test_no_cpu_fallback_without_device(L):
     import torch
 

@@ -344,6 +344,18 @@ def test_cli_is_interchangeable_with_the_reference_cli(tmp_path):
     subprocess.check_call([cli, "-i", str(ref), "-o", str(back2)])                                     # we decode the reference's
     assert back1.read_bytes() == data.tobytes() and back2.read_bytes() == data.tobytes()
     assert subprocess.call([cli, "-i", str(src), "-o", str(ours), "-c", "lz78"], stderr=subprocess.DEVNULL) == 255
+    # the streaming loop proper: a build whose file pieces are 2 blocks reads / compresses / writes this 3-block
+    # file in two overlapped pieces and rewrites the header at the end (mc:4128-4129); same bytes both ways
+    small = build.CLI_SMALL
+    ours2, back3 = tmp_path / "ours2.fcx7", tmp_path / "back3.bin"
+    subprocess.check_call([small, "-i", str(src), "-o", str(ours2), "-c", "lz77"])
+    assert ours2.read_bytes() == ref.read_bytes()
+    subprocess.check_call([small, "-i", str(ref), "-o", str(back3)])
+    assert back3.read_bytes() == data.tobytes()
+    empty = tmp_path / "empty.bin"
+    empty.write_bytes(b"")
+    subprocess.check_call([small, "-i", str(empty), "-o", str(ours2), "-c", "lz77"])
+    assert ours2.read_bytes() == bytes.fromhex(G["file_empty"]["fcx7_hex"])
 
 
 def test_device_context_with_small_batches_and_capacity_error(dc):
@@ -364,3 +376,70 @@ def test_device_context_with_small_batches_and_capacity_error(dc):
     assert bytes(small[-16:].cpu().numpy()) == bytes(16)               # nothing written past / near the end
     _, n2 = dc.compress(d_in, d_out)                                   # the context is still usable
     assert n2 == n
+
+
+def test_records_api_and_large_pipelines_round_trip():
+    """fcx_compress_records_lz77 is the block loop without the header: records of consecutive pieces behind a
+    header are the file.  A 300-block input walks the multi-batch compress pipeline and the decoder's batch
+    ring (batches of <= 128 blocks, three device slots) -- checked against the input, no CPU reference needed
+    at this size (the per-block bytes are pinned by the other tests)."""
+    data = datagen.gen("phrases", (300 << 20) + 4321, seed=3)
+    cut = 77 << 20
+    recs = api.compress_records(data[:cut]) + api.compress_records(data[cut:])
+    nb = (len(data) + (1 << 20) - 1) >> 20
+    head = b"FCX7" + (len(data) & 0xFFFFFFFF).to_bytes(4, "little") + (nb & 0xFFFF).to_bytes(2, "little")
+    blob = api.compress(data)
+    assert blob == head + recs
+    assert api.decompress(blob) == data.tobytes()
+    assert api.decompress_records(recs, nb) == data.tobytes()
+    # pinned host buffers from the library's own allocator take the same path
+    pin_in, pin_out = api.PinnedBuffer(len(data)), api.PinnedBuffer(api.compress_bound(len(data)))
+    pin_in.array[:] = data
+    n = api.compress_into(pin_in.array, pin_out.array)
+    assert pin_out.array[:n].tobytes() == blob
+    pin_in.close(); pin_out.close()
+
+
+def test_device_resident_decode_and_truncated_containers(dc):
+    import torch
+
+    data = datagen.gen("mixed", (5 << 20) + 99, seed=13)
+    blob = np.frombuffer(api.compress(data), np.uint8)
+    offs, end = api.record_offsets(blob, 6, 10)
+    assert end == len(blob)
+    d_file = torch.zeros(len(blob) + 64, dtype=torch.uint8, device="cuda")
+    d_file[: len(blob)] = torch.from_numpy(blob.copy()).cuda()
+    d_out = torch.zeros(6 << 20, dtype=torch.uint8, device="cuda")
+    lens = dc.decompress(d_file, offs, d_out)
+    assert lens.tolist() == [1 << 20] * 5 + [99]
+    assert bytes(d_out[: len(data)].cpu().numpy()) == data.tobytes()
+    for cutoff in (5, 12, len(blob) // 2, len(blob) - 1):
+        with pytest.raises(api.FcxError) as e:
+            api.decompress(blob[:cutoff].tobytes() if cutoff >= 10 else blob[:cutoff].tobytes() + b"")
+        assert e.value.code == -5                                      # FCX_ERR_FORMAT (mc:4139-4152: read errors end the run)
+
+
+def test_no_kernel_writes_outside_its_workspace_arrays():
+    """compute-sanitizer is not available on the GPU pool: every workspace array of a context lies between two
+    guard bands; after the whole pipeline ran over every data family (ragged tail, lazy long-match tiles,
+    literal-only tiles, multi-batch, decode) none of them may have changed."""
+    import torch
+
+    d = api.DeviceCompressor(0, max_batch_blocks=4)
+    try:
+        d.guards(False)
+        for family, nbytes in (("mixed", (9 << 20) + 12345), ("byterun", (2 << 20) + 1), ("zeros", 5000), ("periodic", (1 << 20) + 7),
+                               ("zipf", 1), ("uniform", (1 << 20) - 1)):
+            data = datagen.gen(family, nbytes, seed=17)
+            d_in = _dev(data)
+            d_out = torch.empty(api.compress_bound(len(data)), dtype=torch.uint8, device="cuda")
+            _, n = d.compress(d_in, d_out)
+            blob = d_out[:n].cpu().numpy()
+            nb = (nbytes + (1 << 20) - 1) >> 20
+            offs, _ = api.record_offsets(blob, nb, 10)
+            d_file = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+            d_file[:n] = d_out[:n]
+            d.decompress(d_file, offs, torch.empty(nb << 20, dtype=torch.uint8, device="cuda"))
+            assert d.guards(True) == 0, family
+    finally:
+        d.close()
