@@ -59,7 +59,7 @@ struct Ws {
     uint32_t strmStride[4];
     uint16_t *parseExit;  // [maxBlocks][256 tiles][258] exit offset (0..257) of a tile per entry offset
     uint16_t *tileEntry;  // [maxBlocks][256] offset at which the chain enters each tile
-    uint4 *tileCnt;       // [maxBlocks][256] tokens, matches, Golomb bits (exclusive ranks after the scan)
+    unsigned long long *tileState;   // [maxBlocks][256] look-back status word of each parse tile (fcx_parse.cu)
     uint32_t *blkLen;     // [maxBlocks]
     uint32_t *meta;       // [maxBlocks][M_WORDS]
     uint32_t *segHist;    // [4*maxBlocks][256]

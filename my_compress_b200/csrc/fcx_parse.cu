@@ -10,10 +10,12 @@
 //   k_parse_exits   every tile, for each of the 258 positions a chain can enter it at, the
 //                   position it leaves at (exit function of the tile)
 //   k_parse_entries per block, composes the exit functions tile by tile -> entry of each tile
-//   k_parse_count   every tile walks its part of the chain: tokens, matches, Golomb bits
-//   k_parse_scan    per block, exclusive scan of those counts -> rank of each tile's first token
-//   k_parse_emit    every tile scatters c bytes, flag bits, 11-bit distances and Golomb codes
-//                   to their final bit positions
+//   k_parse_emit    every tile walks its part of the chain ONCE: counts its tokens, matches and
+//                   Golomb bits, publishes them, packs c bytes, flag bits, 11-bit distances and
+//                   Golomb codes into shared memory, learns the rank of its first token from the
+//                   tiles before it (decoupled look-back over one 64-bit status word per tile --
+//                   the device-wide scan of the parse -- while the packing is under way), and
+//                   copies the packed bits to their final bit positions
 // Inside a tile the chain is resolved by a three-level jump table:
 //   J1[i] = first chain position at or beyond the end of i's 16-position mini-tile
 //   J2[i] = first chain position at or beyond the end of i's 256-position mid-tile
@@ -170,90 +172,85 @@ __device__ __forceinline__ void walk_count(const uint8_t *lcb, int e0, int hi, u
     }
 }
 
-// ---- 3: per-tile token / match / Golomb-bit counts --------------------------------------------------
-__global__ void __launch_bounds__(PT_THREADS)
-k_parse_count(const uint32_t *__restrict__ blkLen, const uint8_t *__restrict__ lenCode, Ws ws)
-{
-    __shared__ JumpSmem sm;
-    __shared__ uint32_t red[3][8];
-    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = (int)blkLen[b];
-    const int tb = tile * PT;
-    if (tb >= n) return;
-    const int limit = min(PT, n - tb);
-    if (!tile_has_match(lenCode + (size_t)b * kBlockBytes, tb)) {
-        if (tid == 0) {
-            const int entry = ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile];
-            ws.tileCnt[(size_t)b * kParseTilesPerBlock + tile] = make_uint4((uint32_t)max(limit - entry, 0), 0, 0, 0);
-        }
-        return;
-    }
-    build_jumps(sm, lenCode + (size_t)b * kBlockBytes, tb, limit);
-    resolve_entries(sm, ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile]);
-    uint32_t tok, mat, gb;
-    walk_count(reinterpret_cast<const uint8_t *>(sm.lc), sm.miniEntry[tid], min(tid * 16 + 16, limit), tok, mat, gb);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        tok += __shfl_xor_sync(0xFFFFFFFFu, tok, d);
-        mat += __shfl_xor_sync(0xFFFFFFFFu, mat, d);
-        gb += __shfl_xor_sync(0xFFFFFFFFu, gb, d);
-    }
-    if (lane == 0) { red[0][warp] = tok; red[1][warp] = mat; red[2][warp] = gb; }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t a = 0, c = 0, g = 0;
-        for (int w = 0; w < 8; w++) { a += red[0][w]; c += red[1][w]; g += red[2][w]; }
-        ws.tileCnt[(size_t)b * kParseTilesPerBlock + tile] = make_uint4(a, c, g, 0);
-    }
-}
-
-// ---- 4: per-block exclusive scan over tiles; block totals -> meta ------------------------------------
-__global__ void __launch_bounds__(kParseTilesPerBlock)
-k_parse_scan(const uint32_t *__restrict__ blkLen, Ws ws)
-{
-    __shared__ uint32_t wsum[3][8];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = (int)blkLen[b];
-    const int nTiles = (n + PT - 1) / PT;
-    uint4 *cnt = ws.tileCnt + (size_t)b * kParseTilesPerBlock;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (tid < nTiles) v = cnt[tid];
-    uint32_t a = v.x, c = v.y, g = v.z;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t ta = __shfl_up_sync(0xFFFFFFFFu, a, d), tc = __shfl_up_sync(0xFFFFFFFFu, c, d),
-                       tg = __shfl_up_sync(0xFFFFFFFFu, g, d);
-        if (lane >= d) { a += ta; c += tc; g += tg; }
-    }
-    if (lane == 31) { wsum[0][warp] = a; wsum[1][warp] = c; wsum[2][warp] = g; }
-    __syncthreads();
-    uint32_t ba = 0, bc = 0, bg = 0, ta = 0, tc = 0, tg = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        if (w < warp) { ba += wsum[0][w]; bc += wsum[1][w]; bg += wsum[2][w]; }
-        ta += wsum[0][w]; tc += wsum[1][w]; tg += wsum[2][w];
-    }
-    if (tid < nTiles) cnt[tid] = make_uint4(ba + a - v.x, bc + c - v.y, bg + g - v.z, v.x);   // exclusive bases; w = own tokens
-    if (tid == 0) {
-        const uint32_t G = (tg + 31) >> 5;                        // mc:295-302: last partial word is flushed
-        uint32_t *m = ws.meta + (size_t)b * M_WORDS;
-        m[M_T] = ta; m[M_PC] = tc; m[M_G] = G; m[M_GBITS] = tg;
-        m[M_S0] = (ta + 7) >> 3;                                  // mc:2077-2078
-        m[M_S1] = ta;
-        m[M_S2] = (kPBits * tc) / 8 + 1;                          // mc:2193: one spare byte when divisible
-        m[M_S3] = 4 * G;                                          // mc:2230-2236: words viewed as bytes
-    }
-}
-
-// ---- 5: emit -----------------------------------------------------------------------------------------
+// ---- 3: emit -----------------------------------------------------------------------------------------
 struct EmitSmem {
     JumpSmem j;
     uint32_t xs[(PT + PT_LOOK) / 4];
     uint8_t cbuf[PT + 16];
-    uint32_t fbits[PT / 32 + 4];
+    uint32_t fbits[PT / 32 + 4];          // tile-relative bit streams: bit 0 = the tile's first flag / distance / Golomb bit
     uint32_t pbits[368];
     uint32_t gbits[128];
+    unsigned long long base;              // look-back result: packed exclusive ranks of the tile's first token
 };
+
+// One status word per tile (ws.tileState, zeroed per launch): status << 62 | Golomb bits << 40 | matches << 21 | tokens.
+// Fields are sums over at most one block (tokens <= 2^20, matches <= 2^18, Golomb bits < 2^20), so packed words add
+// without carries between fields.  status 1 = the tile's own counts, 2 = counts of the tile and of all tiles before it.
+constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
+__device__ __forceinline__ unsigned long long ts_pack(uint32_t tok, uint32_t mat, uint32_t gb)
+{
+    return (unsigned long long)tok | ((unsigned long long)mat << 21) | ((unsigned long long)gb << 40);
+}
+__device__ __forceinline__ uint32_t ts_tok(unsigned long long v) { return (uint32_t)v & 0x1FFFFFu; }
+__device__ __forceinline__ uint32_t ts_mat(unsigned long long v) { return (uint32_t)(v >> 21) & 0x7FFFFu; }
+__device__ __forceinline__ uint32_t ts_gb(unsigned long long v) { return (uint32_t)(v >> 40) & 0x1FFFFFu; }
+__device__ __forceinline__ void ts_store(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ts_load(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Decoupled look-back by one warp (all 32 lanes): sum of the counts of tiles 0..tile-1 of this block.  Lane j looks at
+// tile t-j; the nearest word that already holds a prefix ends the walk.  Tiles of a block have consecutive CTA numbers
+// (blockIdx.x runs fastest) and a CTA only ever waits for lower-numbered ones, which were dispatched before it.
+__device__ __forceinline__ unsigned long long tile_lookback(const unsigned long long *row, int tile, int lane)
+{
+    unsigned long long acc = 0;
+    for (int t = tile - 1; t >= 0; t -= 32) {
+        const int idx = t - lane;
+        unsigned long long v;
+        do {
+            v = idx >= 0 ? ts_load(row + idx) : (2ull << 62);           // before tile 0: an empty prefix
+        } while (__any_sync(0xFFFFFFFFu, (v >> 62) == 0));
+        const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+        const int first = incl ? __ffs(incl) - 1 : 32;
+        unsigned long long c = lane <= first ? (v & TS_MASK) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+        acc += c;
+        if (incl) break;
+    }
+    return acc;
+}
+
+// publishes the tile's counts, waits for the ranks of its first token, publishes the running totals; the last tile
+// of a block also writes the block's meta words.  Called by warp 0 (all lanes); returns the packed exclusive ranks.
+__device__ __forceinline__ unsigned long long tile_ranks(const Ws &ws, int b, int tile, int nTiles, int lane, unsigned long long mine)
+{
+    unsigned long long *row = ws.tileState + (size_t)b * kParseTilesPerBlock;
+    if (tile > 0 && lane == 0) ts_store(row + tile, (1ull << 62) | mine);
+    const unsigned long long before = tile_lookback(row, tile, lane);
+    if (lane == 0) {
+        const unsigned long long incl = before + mine;
+        ts_store(row + tile, (2ull << 62) | incl);
+        if (tile == nTiles - 1) {
+            const uint32_t ta = ts_tok(incl), tc = ts_mat(incl), tg = ts_gb(incl);
+            const uint32_t G = (tg + 31) >> 5;                        // mc:295-302: last partial word is flushed
+            uint32_t *m = ws.meta + (size_t)b * M_WORDS;
+            m[M_T] = ta; m[M_PC] = tc; m[M_G] = G; m[M_GBITS] = tg;
+            m[M_S0] = (ta + 7) >> 3;                                  // mc:2077-2078
+            m[M_S1] = ta;
+            m[M_S2] = (kPBits * tc) / 8 + 1;                          // mc:2193: one spare byte when divisible
+            m[M_S3] = 4 * G;                                          // mc:2230-2236: words viewed as bytes
+        }
+    }
+    return before;
+}
 
 // OR `nbits` (<= 32) low bits of v into a zero-initialised shared bit buffer at bit `pos`
 __device__ __forceinline__ void or_bits(uint32_t *buf, uint32_t pos, uint32_t v, int nbits)
@@ -264,17 +261,20 @@ __device__ __forceinline__ void or_bits(uint32_t *buf, uint32_t pos, uint32_t v,
     if (sh + nbits > 32) atomicOr(&buf[w + 1], v >> (32 - sh));
 }
 
-// copy a tile's bit buffer into a pre-zeroed global bit stream at absolute bit position gpos
+// copy a tile's bit buffer (bit 0 = its first bit; zero beyond nbits, one spare word) into a pre-zeroed global bit
+// stream at absolute bit position gpos: the words are shifted into place on the way
 __device__ __forceinline__ void flush_bits(uint32_t *gstream, const uint32_t *buf, unsigned long long gpos, uint32_t nbits)
 {
     if (nbits == 0) return;
     const uint32_t off = (uint32_t)(gpos & 31);
     const unsigned long long w0 = gpos >> 5;
-    const uint32_t total = off + nbits, nWords = (total + 31) >> 5;
+    const uint32_t total = off + nbits, nWords = (total + 31) >> 5, nSrc = (nbits + 31) >> 5;
     for (uint32_t j = threadIdx.x; j < nWords; j += PT_THREADS) {
+        const uint32_t lo = j ? buf[j - 1] : 0u, hi = j < nSrc ? buf[j] : 0u;
+        const uint32_t v = __funnelshift_l(lo, hi, off);              // (hi << off) | (lo >> (32 - off)); off = 0: hi
         const bool partial = (j == 0 && off) || (j == nWords - 1 && (total & 31));
-        if (partial) atomicOr(&gstream[w0 + j], buf[j]);          // word shared with a neighbouring tile
-        else gstream[w0 + j] = buf[j];
+        if (partial) atomicOr(&gstream[w0 + j], v);                   // word shared with a neighbouring tile
+        else gstream[w0 + j] = v;
     }
 }
 
@@ -287,6 +287,7 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     const int n = (int)blkLen[b];
     const int tb = tile * PT;
     if (tb >= n) return;
+    const int nTiles = (n + PT - 1) / PT;
     const int limit = min(PT, n - tb);
     const uint8_t *x = in + (size_t)b * kBlockBytes;
     const uint16_t *dsG = dist + (size_t)b * kBlockBytes;
@@ -294,23 +295,40 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
         // every token is a literal: c = the bytes themselves, flags = a run of ones at the tile's token rank
         const int entry = ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile];
         const uint32_t tileTok = (uint32_t)max(limit - entry, 0);
-        const uint4 bases = ws.tileCnt[(size_t)b * kParseTilesPerBlock + tile];
-        const uint8_t *src = x + tb + entry;
-        uint8_t *cOut = ws.strm[1] + (size_t)b * ws.strmStride[1] + bases.x;
+        // the tile's bytes travel to shared memory while warp 0 asks the tiles before this one for the token rank
+        {
+            const int pos = tb + tid * 16;
+            uint4 q;
+            if (pos + 16 <= n) q = *reinterpret_cast<const uint4 *>(x + pos);
+            else {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if (pos + k < n) w[k >> 2] |= (uint32_t)x[pos + k] << ((k & 3) * 8);
+                q = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            reinterpret_cast<uint4 *>(sm.xs)[tid] = q;
+        }
+        if (warp == 0) {
+            const unsigned long long r = tile_ranks(ws, b, tile, nTiles, lane, ts_pack(tileTok, 0, 0));
+            if (lane == 0) sm.base = r;
+        }
+        __syncthreads();
+        const uint32_t baseTok = ts_tok(sm.base);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(sm.xs) + entry;
+        uint8_t *cOut = ws.strm[1] + (size_t)b * ws.strmStride[1] + baseTok;
         // byte copy between two unaligned ranges: 4-byte stores on the destination's alignment, bytes at the edges
         const uint32_t head = min(tileTok, (uint32_t)((4u - ((uint32_t)(size_t)cOut & 3u)) & 3u));
         if ((uint32_t)tid < head) cOut[tid] = src[tid];
         const uint32_t nW = (tileTok - head) >> 2;
-        for (uint32_t k = tid; k < nW; k += PT_THREADS) {
-            const uint8_t *q = src + head + 4 * k;
-            reinterpret_cast<uint32_t *>(cOut + head)[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-        }
+        for (uint32_t k = tid; k < nW; k += PT_THREADS)
+            reinterpret_cast<uint32_t *>(cOut + head)[k] = ld32u(sm.xs, (int)(entry + head + 4 * k));
         const uint32_t done = head + 4 * nW;
         if ((uint32_t)tid < tileTok - done) cOut[done + tid] = src[done + tid];
-        // flag bits [bases.x, bases.x + tileTok) of the (pre-zeroed) bitmap stream
+        // flag bits [baseTok, baseTok + tileTok) of the (pre-zeroed) bitmap stream
         if (tileTok) {
             uint32_t *fs = reinterpret_cast<uint32_t *>(ws.strm[0] + (size_t)b * ws.strmStride[0]);
-            const uint32_t b0 = bases.x, b1 = bases.x + tileTok;            // bit range
+            const uint32_t b0 = baseTok, b1 = baseTok + tileTok;             // bit range
             const uint32_t w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
             for (uint32_t w = w0 + tid; w <= w1; w += PT_THREADS) {
                 uint32_t m = 0xFFFFFFFFu;
@@ -368,12 +386,15 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     const uint32_t exP = baseP + incP - packed;
     uint32_t tokIdx = exP & 0xFFFF, matIdx = exP >> 16, gOff = baseG + incG - myGb;
     const uint32_t tileTok = tileP & 0xFFFF, tileMat = tileP >> 16;
+    // the tile's counts are known: tell the tiles behind this one before the packing starts (status 1; tile 0 has
+    // nothing to wait for and publishes its prefix right away)
+    unsigned long long *row = ws.tileState + (size_t)b * kParseTilesPerBlock;
+    const unsigned long long mine = ts_pack(tileTok, tileMat, tileG);
+    if (tid == 0 && tile > 0) ts_store(row + tile, (1ull << 62) | mine);
 
-    const uint4 bases = ws.tileCnt[(size_t)b * kParseTilesPerBlock + tile];      // exclusive tok / mat / gbit ranks
-    const uint32_t fOff = bases.x & 31, pOff = (kPBits * bases.y) & 31, gOffBits = bases.z & 31;
     // A thread's tokens have consecutive ranks, so its flag bits (<= 16) and packed distances
     // (<= 5 x 11 bits) are contiguous: gather them in registers and merge once, instead of one
-    // shared-memory atomic per token.
+    // shared-memory atomic per token.  Bit positions are relative to the tile's first token.
     const uint32_t tok0 = tokIdx, mat0 = matIdx;
     uint32_t flagReg = 0;
     unsigned long long pReg = 0;
@@ -384,7 +405,7 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
             flagReg |= 1u << (tokIdx - tok0);                                     // mc:2087-2089: bit set = literal
         } else {
             pReg |= (unsigned long long)dsG[tb + e] << (kPBits * (matIdx - mat0));  // mc:1301-1309
-            const uint32_t gp = gOffBits + gOff;
+            const uint32_t gp = gOff;
             const int q = len >> 2;                                               // mc:267-269: q ones, 0, 2 remainder bits
             if (q <= 29) {                                                        // whole code fits 32 bits
                 or_bits(sm.gbits, gp, ((1u << q) - 1u) | ((uint32_t)(len & 3) << (q + 1)), q + 3);
@@ -399,19 +420,25 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
         tokIdx++;
         e += len + 1;
     }
-    if (flagReg) or_bits(sm.fbits, fOff + tok0, flagReg, 16);
+    if (flagReg) or_bits(sm.fbits, tok0, flagReg, 16);
     if (matIdx > mat0) {
-        const uint32_t pp = pOff + kPBits * mat0;
+        const uint32_t pp = kPBits * mat0;
         or_bits(sm.pbits, pp, (uint32_t)pReg, 32);
         if (matIdx - mat0 > 2) or_bits(sm.pbits, pp + 32, (uint32_t)(pReg >> 32), 32);
     }
+    // ranks of the tile's first token: by now the tiles before this one have usually published theirs
+    if (warp == 0) {
+        const unsigned long long r = tile_ranks(ws, b, tile, nTiles, lane, mine);
+        if (lane == 0) sm.base = r;
+    }
     __syncthreads();
-    uint8_t *cOut = ws.strm[1] + (size_t)b * ws.strmStride[1] + bases.x;
+    const uint32_t baseTok = ts_tok(sm.base), baseMat = ts_mat(sm.base), baseGb = ts_gb(sm.base);
+    uint8_t *cOut = ws.strm[1] + (size_t)b * ws.strmStride[1] + baseTok;
     for (uint32_t k = tid; k < tileTok; k += PT_THREADS) cOut[k] = sm.cbuf[k];
-    flush_bits(reinterpret_cast<uint32_t *>(ws.strm[0] + (size_t)b * ws.strmStride[0]), sm.fbits, bases.x, tileTok);
+    flush_bits(reinterpret_cast<uint32_t *>(ws.strm[0] + (size_t)b * ws.strmStride[0]), sm.fbits, baseTok, tileTok);
     flush_bits(reinterpret_cast<uint32_t *>(ws.strm[2] + (size_t)b * ws.strmStride[2]), sm.pbits,
-               (unsigned long long)kPBits * bases.y, kPBits * tileMat);
-    flush_bits(reinterpret_cast<uint32_t *>(ws.strm[3] + (size_t)b * ws.strmStride[3]), sm.gbits, bases.z, tileG);
+               (unsigned long long)kPBits * baseMat, kPBits * tileMat);
+    flush_bits(reinterpret_cast<uint32_t *>(ws.strm[3] + (size_t)b * ws.strmStride[3]), sm.gbits, baseGb, tileG);
 }
 
 void parse_init()
@@ -429,10 +456,9 @@ int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32
     cudaMemsetAsync(ws.strm[3], 0, (size_t)nBlocks * ws.strmStride[3], st);
     k_parse_exits<<<grid, PT_THREADS, 0, st>>>(blkLen, ws.lenCode, ws);
     k_parse_entries<<<nBlocks, PE_THREADS, PE_TABLE * sizeof(uint16_t) + 16, st>>>(blkLen, ws);
-    k_parse_count<<<grid, PT_THREADS, 0, st>>>(blkLen, ws.lenCode, ws);
-    k_parse_scan<<<nBlocks, kParseTilesPerBlock, 0, st>>>(blkLen, ws);
+    cudaMemsetAsync(ws.tileState, 0, (size_t)nBlocks * kParseTilesPerBlock * sizeof(unsigned long long), st);
     k_parse_emit<<<grid, PT_THREADS, 0, st>>>(in, blkLen, ws.lenCode, ws.dist, ws);
-    return 5;
+    return 3;
 }
 
 } // namespace fcx
