@@ -339,7 +339,7 @@ extern "C" int fcx_decompress_lz77_device(fcx_ctx *c, const uint8_t *d_file, con
     if (nBlocks == 0) return FCX_OK;
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    constexpr uint32_t kBatch = 128;                      // blocks decoded per launch: bounds the scratch
+    constexpr uint32_t kBatch = 1024;                     // blocks decoded per launch: bounds the scratch (2.3 MB per block)
     const size_t per = decode_scratch_per_block();
     if (!c->decScratch) {
         CK(cudaMalloc(&c->decScratch, per * kBatch + 256));

@@ -6,16 +6,23 @@
 // reference produces, including a single-symbol stream decoding to zeros
 // and the "Fatal Error" early stop when matches run out (mc:2337-2340).
 //
-// The format has no resynchronisation points, so the sequential dependency of a prefix-coded
-// stream is broken speculatively (see spec_decode): one CTA per block, its 128 lanes decode
-// the four Huffman sections one after the other (11-bit look-up table in shared memory, tree
-// walk for longer codes), then the Golomb stream of l values with the same scheme.  All lanes then
-// gather 1024 tokens at a time into shared memory (flag bits -> match ranks by popc and a scan)
-// and warp 0 replays them 32 per trip: a warp scan of len+1 gives every token its output
-// position, tokens whose source lies before the batch copy in parallel
-// inside a 16 KB shared ring of recent output, the few that reach into the batch follow in
-// order (overlapping copies use source offset k mod p), and finished words are flushed to HBM
-// with coalesced stores.
+// Three kernels per batch of blocks:
+//   k_dec_parse     one thread per block walks the payload's section headers (offsets, symbol counts, tree
+//                   sizes, word counts) into a small per-block record and rejects truncated payloads
+//   k_dec_sections  one CTA per (section, block): the four Huffman sections of a block decode side by side.
+//                   The format has no resynchronisation points, so the sequential dependency of a prefix-coded
+//                   stream is broken speculatively (see spec_decode): every lane takes the next 512 bits, lane
+//                   0 starts on a code boundary, the others guess, and lanes re-decode until nobody's start
+//                   moves (prefix codes fall into step after a few symbols).  11-bit look-up table in shared
+//                   memory, tree walk for longer codes.
+//   k_dec_replay    one CTA per block: the Golomb stream of match lengths by the same speculative scheme, then
+//                   the token replay, BYTE-parallel: for a batch of up to 2048 tokens / 8 KiB of output a scan
+//                   of len+1 places every token, every output byte gets a pointer to the byte it copies
+//                   (itself for a literal), pointer doubling over the batch collapses chains of copies -- a
+//                   byte ends up pointing either before the batch or at a literal; at most 13 rounds whatever
+//                   the data, one or two in practice because the encoder prefers the farthest match -- and all
+//                   bytes are then fetched at once.  A 16 KiB shared ring holds the window and the batch;
+//                   finished words leave for HBM with coalesced stores.
 // Malformed payloads that would send the reference out of bounds yield length 0xFFFFFFFF;
 // a match length above 257 (the encoder's maximum), a distance of 0 or a block that would decode to more
 // than 1 MiB (the reference tolerates 8 bytes more) is treated as malformed.
@@ -30,54 +37,95 @@ constexpr size_t DEC_OFF_PK = DEC_OFF_CS + 1048576 + 256;
 constexpr size_t DEC_OFF_GB = DEC_OFF_PK + 360704 + 256;
 constexpr size_t DEC_OFF_LV = DEC_OFF_GB + 105216 + 256;          // u16 l value per match
 constexpr uint32_t DEC_MAX_PC = kBlockBytes / 4 + 1;
-constexpr size_t DEC_SCRATCH = DEC_OFF_LV + 2 * (size_t)DEC_MAX_PC + 254;
-static_assert(DEC_SCRATCH % 16 == 0 && DEC_OFF_LV % 16 == 0, "scratch regions stay 16-byte aligned");
+constexpr size_t DEC_OFF_META = DEC_OFF_LV + 2 * (size_t)DEC_MAX_PC + 254;
+constexpr size_t DEC_SCRATCH = DEC_OFF_META + 256;
+static_assert(DEC_SCRATCH % 16 == 0 && DEC_OFF_LV % 16 == 0 && DEC_OFF_META % 16 == 0, "scratch regions stay 16-byte aligned");
 
 size_t decode_scratch_per_block() { return DEC_SCRATCH; }
 
-constexpr int DEC_THREADS = 128;
+// per-block record written by k_dec_parse (at DEC_OFF_META of the block's scratch)
+struct DecMeta {
+    uint32_t T, Pc, G, bad;
+    uint32_t secOff[4], secCnt[4], secTn[4], secW[4], secRaw[4];
+    uint32_t nL;                       // l values the Golomb stream really held (k_dec_replay)
+};
+static_assert(sizeof(DecMeta) <= 256, "the record fits its scratch slot");
+
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int DEC_LUT_BITS = 11;
 constexpr int DEC_LUT = 1 << DEC_LUT_BITS;
-constexpr uint32_t DEC_RING = 16384;                              // >= 2047 (window) + 32 * 258 (one batch)
 constexpr uint32_t DEC_SUB_BITS = 512;                            // bits a lane decodes per trip
 constexpr uint32_t DEC_FIN = 0xFFFFFFFFu;                         // "the stream ended inside this subsequence"
-constexpr int DEC_SUPER = 8 * DEC_THREADS;                        // tokens gathered per trip
-constexpr uint32_t DEC_TOK_NONE = 0xFFFD, DEC_TOK_STOP = 0xFFFE, DEC_TOK_BAD = 0xFFFF;
-
-struct DecSmem {
-    uint8_t ring[DEC_RING];              // replay: the most recent output bytes, addressed by position & (DEC_RING-1)
-    uint16_t lut[DEC_LUT];               // current section: len << 8 | symbol for codes of <= 11 bits, else 0
-    uint8_t pair[512];
-    uint8_t map[64];
-    uint32_t endS[DEC_THREADS];          // bit position at which each lane's subsequence ends (DEC_FIN: stream over)
-    uint32_t warpTot[DEC_THREADS / 32];
-    uint32_t secOff[4], secCnt[4], secTn[4], secW[4], secRaw[4];
-    uint32_t T, Pc, G, bad, nL, fin;
-    uint16_t tokL[DEC_SUPER];            // replay: match length per token (0 literal-only), or a DEC_TOK_* marker
-    uint16_t tokP[DEC_SUPER];            //         distance
-    uint8_t tokC[DEC_SUPER];             //         literal byte
-};
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p)
 {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
+// =========================================================================================
+// 1: section headers
+// =========================================================================================
 // Parses one section header at payload offset `at`; returns the offset just past the section.
-__device__ uint32_t parse_section(DecSmem &sm, int k, const uint8_t *pl, uint32_t plen, uint32_t at, uint32_t cnt)
+__device__ uint32_t parse_section(DecMeta &m, int k, const uint8_t *pl, uint32_t plen, uint32_t at, uint32_t cnt)
 {
-    sm.secCnt[k] = cnt; sm.secRaw[k] = 0; sm.secOff[k] = at; sm.secTn[k] = 0; sm.secW[k] = 0;
-    if (at + 5 > plen) { sm.bad = 1; return at; }
+    m.secCnt[k] = cnt; m.secRaw[k] = 0; m.secOff[k] = at; m.secTn[k] = 0; m.secW[k] = 0;
+    if (at + 5 > plen) { m.bad = 1; return at; }
     const uint32_t Tn = pl[at];
     const uint32_t mapB = (2 * Tn + 7) / 8;
     const uint32_t wAt = at + 1 + mapB + 2 * Tn;
-    if (wAt + 4 > plen) { sm.bad = 1; return at; }
+    if (wAt + 4 > plen) { m.bad = 1; return at; }
     const uint32_t W = rd32(pl + wAt);
-    if ((unsigned long long)wAt + 4 + 4ull * W > plen) { sm.bad = 1; return at; }
-    sm.secTn[k] = Tn; sm.secW[k] = W;
+    if ((unsigned long long)wAt + 4 + 4ull * W > plen) { m.bad = 1; return at; }
+    m.secTn[k] = Tn; m.secW[k] = W;
     return wAt + 4 + 4 * W;
 }
 
+__global__ void __launch_bounds__(128)
+k_dec_parse(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff, uint32_t nBlocks,
+            uint8_t *__restrict__ scratchAll, size_t scratchPerBlock)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nBlocks) return;
+    const uint8_t *rec = file + recOff[b];
+    const uint32_t plen = rd32(rec);
+    const uint8_t *pl = rec + 4;
+    DecMeta m;
+    m.T = m.Pc = m.G = m.bad = m.nL = 0;
+    for (int k = 0; k < 4; k++) { m.secOff[k] = m.secCnt[k] = m.secTn[k] = m.secW[k] = m.secRaw[k] = 0; }
+    if (plen < 4) m.bad = 1;
+    else {
+        const uint32_t T = rd32(pl);
+        m.T = T;
+        if (T > kBlockBytes) m.bad = 1;
+        else {
+            uint32_t at = 4;
+            const uint32_t mapB = (T + 7) / 8;
+            if (mapB > 1) at = parse_section(m, 0, pl, plen, at, mapB);            // mc:2273-2276
+            else { m.secRaw[0] = 1; m.secOff[0] = at; m.secCnt[0] = mapB;
+                   if (at + mapB > plen) m.bad = 1; at += mapB; }                    // mc:2277-2280
+            if (!m.bad) at = parse_section(m, 1, pl, plen, at, T);                 // mc:2283
+            if (!m.bad && at + 4 <= plen) {
+                m.Pc = rd32(pl + at); at += 4;                                     // mc:2286
+                if (m.Pc > DEC_MAX_PC) m.bad = 1;
+            } else m.bad = 1;
+            if (!m.bad) at = parse_section(m, 2, pl, plen, at, (kPBits * m.Pc) / 8 + 1);   // mc:2290-2292
+            if (!m.bad && at + 4 <= plen) {
+                m.G = rd32(pl + at); at += 4;                                      // mc:2302
+                if (m.G > 105216 / 4) m.bad = 1;
+            } else m.bad = 1;
+            if (!m.bad) {
+                if (m.G) at = parse_section(m, 3, pl, plen, at, m.G * 4);          // mc:2308
+                else { m.secCnt[3] = 0; m.secW[3] = 0; m.secTn[3] = 0; m.secRaw[3] = 0; m.secOff[3] = at; }   // App. B8
+            }
+        }
+    }
+    *reinterpret_cast<DecMeta *>(scratchAll + (size_t)b * scratchPerBlock + DEC_OFF_META) = m;
+}
+
+// =========================================================================================
+// speculative parallel decode of one prefix-coded stream by a 256-lane CTA
+// =========================================================================================
 // ---- per-lane bit cursor over little-endian 32-bit words at any byte address -------------------
 template <bool kConst>
 struct LaneBits {
@@ -160,15 +208,19 @@ struct GolombCodec {
     }
 };
 
-// Speculative parallel decode of one prefix-coded stream by the whole CTA.  Every lane takes the
-// next DEC_SUB_BITS bits; lane 0 starts on a code boundary, the others guess.  A lane decodes until
-// it crosses into the next lane's bits and publishes where it ended; a lane whose predecessor ended
-// somewhere else than where it started decodes again from there, until nobody moves (prefix codes
+struct SpecSmem {
+    uint32_t endS[DEC_THREADS];          // bit position at which each lane's subsequence ends (DEC_FIN: stream over)
+    uint32_t warpTot[DEC_WARPS];
+};
+
+// Every lane takes the next DEC_SUB_BITS bits; lane 0 starts on a code boundary, the others guess.  A lane
+// decodes until it crosses into the next lane's bits and publishes where it ended; a lane whose predecessor
+// ended somewhere else than where it started decodes again from there, until nobody moves (prefix codes
 // fall into step after a few symbols, so this is one or two rounds; by induction over the lanes the
 // fixed point is the sequential decode whatever the data).  A scan of the symbol counts then gives
 // every lane its output offset for the writing pass.  Returns the symbols produced (<= cnt).
 template <class Codec, class Bits, class Emit>
-__device__ uint32_t spec_decode(DecSmem &sm, const Codec &cd, Bits lb, uint32_t cnt, Emit emit, bool &bad)
+__device__ uint32_t spec_decode(SpecSmem &sm, const Codec &cd, Bits lb, uint32_t cnt, Emit emit, bool &bad)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t totalBits = lb.W * 32u;
@@ -209,7 +261,7 @@ __device__ uint32_t spec_decode(DecSmem &sm, const Codec &cd, Bits lb, uint32_t 
         __syncthreads();
         uint32_t off = inc - myN, total = 0;
 #pragma unroll
-        for (int w = 0; w < DEC_THREADS / 32; w++) { const uint32_t v = sm.warpTot[w]; if (w < warp) off += v; total += v; }
+        for (int w = 0; w < DEC_WARPS; w++) { const uint32_t v = sm.warpTot[w]; if (w < warp) off += v; total += v; }
         const uint32_t first = outBase + off;
         // the sequential decoder would walk into this lane's malformed code unless cnt stops it earlier
         if (myBad && first + myN < cnt) bad = true;
@@ -231,236 +283,292 @@ __device__ uint32_t spec_decode(DecSmem &sm, const Codec &cd, Bits lb, uint32_t 
     return min(outBase, cnt);
 }
 
+// =========================================================================================
+// 2: the four Huffman sections, one CTA each
+// =========================================================================================
+struct SecSmem {
+    SpecSmem spec;
+    uint16_t lut[DEC_LUT];               // len << 8 | symbol for codes of <= 11 bits, else 0
+    uint8_t pair[512];
+    uint8_t map[64];
+};
+
 __global__ void __launch_bounds__(DEC_THREADS)
-k_decode(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff, uint8_t *__restrict__ out,
-         uint32_t *__restrict__ outLen, uint8_t *__restrict__ scratchAll, size_t scratchPerBlock)
+k_dec_sections(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff,
+               uint8_t *__restrict__ scratchAll, size_t scratchPerBlock)
 {
-    __shared__ DecSmem sm;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint8_t *rec = file + recOff[b];
-    const uint32_t plen = rd32(rec);
-    const uint8_t *pl = rec + 4;
+    __shared__ SecSmem sm;
+    const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     uint8_t *scr = scratchAll + (size_t)b * scratchPerBlock;
-    uint8_t *dst[4] = {scr + DEC_OFF_BM, scr + DEC_OFF_CS, scr + DEC_OFF_PK, scr + DEC_OFF_GB};
+    DecMeta *meta = reinterpret_cast<DecMeta *>(scr + DEC_OFF_META);
+    if (meta->bad) return;
+    const uint8_t *pl = file + recOff[b] + 4;
+    const size_t dstOff = k == 0 ? DEC_OFF_BM : k == 1 ? DEC_OFF_CS : k == 2 ? DEC_OFF_PK : DEC_OFF_GB;
+    uint8_t *d = scr + dstOff;
+    const uint32_t at = meta->secOff[k], cnt = meta->secCnt[k], Tn = meta->secTn[k], W = meta->secW[k];
+    if (meta->secRaw[k]) {
+        for (uint32_t i = tid; i < cnt; i += DEC_THREADS) d[i] = pl[at + i];
+        return;
+    }
+    // Tn == 0 (single-symbol stream): nothing is decoded, the zero-filled buffer stands (App. B1)
+    if (!(cnt && Tn && W)) return;
+    const uint32_t mapB = (2 * Tn + 7) / 8;
+    for (uint32_t i = tid; i < mapB; i += DEC_THREADS) sm.map[i] = pl[at + 1 + i];
+    for (uint32_t i = tid; i < 2 * Tn; i += DEC_THREADS) sm.pair[i] = pl[at + 1 + mapB + i];
+    __syncthreads();
+    const uint32_t R = Tn + 1, root = Tn - 1;                    // root = last stored node (mc:945-946)
+    for (uint32_t idx = tid; idx < (uint32_t)DEC_LUT; idx += DEC_THREADS) {
+        uint32_t node = root, e = 0;
+        for (int bit = 0; bit < DEC_LUT_BITS; bit++) {
+            const uint32_t c = 2 * node + ((idx >> bit) & 1u);
+            const uint32_t ci = sm.pair[c];
+            if (!((sm.map[c >> 3] >> (c & 7)) & 1)) { e = ((uint32_t)(bit + 1) << 8) | ci; break; }
+            node = ci - (256 - R);
+            if (node >= Tn) break;                               // malformed: the exact walk reports it if it is ever reached
+        }
+        sm.lut[idx] = (uint16_t)e;
+    }
+    __syncthreads();
+    HuffCodec cd{sm.lut, sm.pair, sm.map, Tn, R, root};
+    LaneBits<true> lb;
+    lb.open(pl + at + 1 + mapB + 2 * Tn + 4, W);
+    bool bad = false;
+    spec_decode(sm.spec, cd, lb, cnt, [d](uint32_t i, uint32_t sym) { d[i] = (uint8_t)sym; }, bad);
+    if (bad) meta->bad = 1;                                      // same value from whoever writes it
+}
+
+// =========================================================================================
+// 3: match lengths, then the byte-parallel token replay
+// =========================================================================================
+constexpr uint32_t RP_RING = 16384;                 // >= 2047 (window) + RP_BYTES (one batch)
+constexpr uint32_t RP_MASK = RP_RING - 1;
+constexpr uint32_t RP_BYTES = 8192;                 // output bytes per batch at most
+constexpr int RP_PER = 8;                           // tokens a thread gathers: one flag byte
+constexpr uint32_t RP_TOKENS = DEC_THREADS * RP_PER;      // 2048
+constexpr uint32_t RP_NONE = 0xFFFD, RP_STOP = 0xFFFE, RP_BADTOK = 0xFFFF;
+static_assert(RP_BYTES + 2047 + 258 <= RP_RING, "window + batch fit the ring");
+
+struct ReplaySmem {
+    SpecSmem spec;
+    alignas(16) uint8_t ring[RP_RING];   // the most recent output bytes, addressed by position & RP_MASK
+    int16_t src[RP_BYTES + 264];         // per output byte of the batch: batch-relative position it copies from (itself: literal)
+    uint16_t tokL[RP_TOKENS];            // match length per token (0: literal only), or an RP_* marker
+    uint16_t tokP[RP_TOKENS];            // distance
+    uint16_t tokPos[RP_TOKENS];          // batch-relative output position of the token
+    uint32_t warpA[DEC_WARPS], warpB[DEC_WARPS];
+    uint32_t firstStop, firstBad, nTake, takeBytes, takeMatches, bad;
+};
+
+__global__ void __launch_bounds__(DEC_THREADS)
+k_dec_replay(uint8_t *__restrict__ out, uint32_t *__restrict__ outLen, uint8_t *__restrict__ scratchAll, size_t scratchPerBlock)
+{
+    extern __shared__ __align__(16) uint8_t rp_smem_raw[];
+    ReplaySmem &sm = *reinterpret_cast<ReplaySmem *>(rp_smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *scr = scratchAll + (size_t)b * scratchPerBlock;
+    DecMeta *meta = reinterpret_cast<DecMeta *>(scr + DEC_OFF_META);
+    if (meta->bad) { if (tid == 0) outLen[b] = DEC_BAD; return; }
+    const uint8_t *bm = scr + DEC_OFF_BM, *cs = scr + DEC_OFF_CS, *pk = scr + DEC_OFF_PK;
     uint16_t *lv = reinterpret_cast<uint16_t *>(scr + DEC_OFF_LV);
     uint8_t *o = out + (size_t)b * kBlockBytes;                    // blocks sit back to back: a full block is 1 MiB
+    const uint32_t T = meta->T, Pc = meta->Pc, G = meta->G;
 
-    if (tid == 0) {
-        sm.bad = 0; sm.Pc = 0; sm.G = 0; sm.T = 0; sm.nL = 0;
-        if (plen < 4) sm.bad = 1;
-        else {
-            const uint32_t T = rd32(pl);
-            sm.T = T;
-            if (T > kBlockBytes) sm.bad = 1;
-            else {
-                uint32_t at = 4;
-                const uint32_t mapB = (T + 7) / 8;
-                if (mapB > 1) at = parse_section(sm, 0, pl, plen, at, mapB);            // mc:2273-2276
-                else { sm.secRaw[0] = 1; sm.secOff[0] = at; sm.secCnt[0] = mapB; sm.secW[0] = 0; sm.secTn[0] = 0;
-                       if (at + mapB > plen) sm.bad = 1; at += mapB; }                  // mc:2277-2280
-                if (!sm.bad) at = parse_section(sm, 1, pl, plen, at, T);                // mc:2283
-                if (!sm.bad && at + 4 <= plen) {
-                    sm.Pc = rd32(pl + at); at += 4;                                     // mc:2286
-                    if (sm.Pc > DEC_MAX_PC) sm.bad = 1;
-                } else sm.bad = 1;
-                if (!sm.bad) at = parse_section(sm, 2, pl, plen, at, (kPBits * sm.Pc) / 8 + 1);   // mc:2290-2292
-                if (!sm.bad && at + 4 <= plen) {
-                    sm.G = rd32(pl + at); at += 4;                                      // mc:2302
-                    if (sm.G > 105216 / 4) sm.bad = 1;
-                } else sm.bad = 1;
-                if (!sm.bad) {
-                    if (sm.G) at = parse_section(sm, 3, pl, plen, at, sm.G * 4);        // mc:2308
-                    else { sm.secCnt[3] = 0; sm.secW[3] = 0; sm.secTn[3] = 0; sm.secRaw[3] = 0; sm.secOff[3] = at; }   // App. B8
-                }
-            }
-        }
+    // ---- the l values (golomb_rice_decode, mc:309-358) -----------------------------------------------------
+    uint32_t nL = 0;
+    if (G && Pc) {
+        GolombCodec gc;
+        LaneBits<false> gbits;
+        gbits.open(scr + DEC_OFF_GB, G);
+        bool gbad = false;
+        nL = spec_decode(sm.spec, gc, gbits, Pc, [lv](uint32_t i, uint32_t sym) { lv[i] = (uint16_t)sym; }, gbad);
     }
-    __syncthreads();
-    if (sm.bad) { if (tid == 0) outLen[b] = DEC_BAD; return; }
+    if (tid == 0) sm.bad = 0;
+    __syncthreads();                                                // lv is read by other lanes from here on
 
-    // ---- phase 1: the four sections one after the other, all lanes on each; then the l values ------
-    for (int k = 0; k < 4; k++) {
-        __syncthreads();                                             // the previous section's table is no longer in use
-        const uint32_t at = sm.secOff[k], cnt = sm.secCnt[k], Tn = sm.secTn[k], W = sm.secW[k];
-        if (sm.secRaw[k]) {
-            for (uint32_t i = tid; i < cnt; i += DEC_THREADS) dst[k][i] = pl[at + i];
-            continue;
-        }
-        // Tn == 0 (single-symbol stream): nothing is decoded, the zero-filled buffer stands (App. B1)
-        if (!(cnt && Tn && W)) continue;
-        const uint32_t mapB = (2 * Tn + 7) / 8;
-        for (uint32_t i = tid; i < mapB; i += DEC_THREADS) sm.map[i] = pl[at + 1 + i];
-        for (uint32_t i = tid; i < 2 * Tn; i += DEC_THREADS) sm.pair[i] = pl[at + 1 + mapB + i];
-        __syncthreads();
-        const uint32_t R = Tn + 1, root = Tn - 1;                    // root = last stored node (mc:945-946)
-        for (uint32_t idx = tid; idx < (uint32_t)DEC_LUT; idx += DEC_THREADS) {
-            uint32_t node = root, e = 0;
-            for (int bit = 0; bit < DEC_LUT_BITS; bit++) {
-                const uint32_t c = 2 * node + ((idx >> bit) & 1u);
-                const uint32_t ci = sm.pair[c];
-                if (!((sm.map[c >> 3] >> (c & 7)) & 1)) { e = ((uint32_t)(bit + 1) << 8) | ci; break; }
-                node = ci - (256 - R);
-                if (node >= Tn) break;                               // malformed: the exact walk reports it if it is ever reached
-            }
-            sm.lut[idx] = (uint16_t)e;
-        }
-        __syncthreads();
-        HuffCodec cd{sm.lut, sm.pair, sm.map, Tn, R, root};
-        LaneBits<true> lb;
-        lb.open(pl + at + 1 + mapB + 2 * Tn + 4, W);
-        uint8_t *d = dst[k];
-        bool bad = false;
-        spec_decode(sm, cd, lb, cnt, [d](uint32_t i, uint32_t sym) { d[i] = (uint8_t)sym; }, bad);
-        if (bad) sm.bad = 1;
-    }
-    __syncthreads();
-    if (sm.bad) { if (tid == 0) outLen[b] = DEC_BAD; return; }
-    {
-        uint32_t nL = 0;
-        if (sm.G && sm.Pc) {
-            GolombCodec gc;
-            LaneBits<false> gbits;
-            gbits.open(dst[3], sm.G);
-            bool bad = false;
-            nL = spec_decode(sm, gc, gbits, sm.Pc, [lv](uint32_t i, uint32_t sym) { lv[i] = (uint16_t)sym; }, bad);
-        }
-        if (tid == 0) sm.nL = nL;
-    }
-    __syncthreads();
-
-    // ---- phase 2: token replay (my_LZ77_decompress, mc:1716-1735) -------------------------------------
-    // 1024 tokens at a time: all lanes gather (len, distance, literal) of eight tokens each into shared
-    // memory (flag bits -> match ranks by popc and a CTA scan, then independent loads), warp 0 replays
-    // them 32 per trip.
-    const uint32_t T = sm.T, Pc = sm.Pc, nL = sm.nL;
-    const uint8_t *bm = dst[0], *cs = dst[1], *pk = dst[2];
+    // ---- token replay (my_LZ77_decompress, mc:1716-1735) -----------------------------------------------------
     uint8_t *ring = sm.ring;
     uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
-    constexpr uint32_t RM = DEC_RING - 1;
-    uint32_t cur = 0, mBase = 0, flushed = 0;                        // cur / flushed live in warp 0
-    bool bad = false;
-    if (tid == 0) sm.fin = 0;
-    for (uint32_t tS = 0; tS < T; tS += DEC_SUPER) {
-        // ---- gather -------------------------------------------------------------------------------------
-        const uint32_t tb = tS + 8u * tid;
-        const uint32_t nvalid = tb < T ? min(8u, T - tb) : 0u;
-        const uint32_t flags = nvalid ? (uint32_t)__ldcg(bm + (tb >> 3)) : 0xFFu;
+    uint32_t cur = 0, mBase = 0, flushed = 0, tS = 0;               // CTA-uniform
+    while (tS < T) {
+        // ---- gather up to 2048 tokens: flag bits -> match ranks (popc + scan) -> length, distance ----------------
+        const uint32_t tb = tS + (uint32_t)RP_PER * tid;
+        const uint32_t nvalid = tb < T ? min((uint32_t)RP_PER, T - tb) : 0u;
+        uint32_t flags = 0xFFu;
+        if (nvalid) {
+            const uint32_t by = tb >> 3, sh = tb & 7;                // the batch may start inside a flag byte
+            flags = (((uint32_t)__ldcg(bm + by) | ((uint32_t)__ldcg(bm + by + 1) << 8)) >> sh) & 0xFFu;
+        }
         const uint32_t zmask = ~flags & ((1u << nvalid) - 1u);       // match tokens among mine
-        uint32_t inc = (uint32_t)__popc(zmask);
-        const uint32_t mine = inc;
+        if (tid == 0) { sm.firstStop = RP_TOKENS; sm.firstBad = RP_TOKENS; sm.nTake = RP_TOKENS; sm.takeMatches = 0; }
+        const bool anyMatch = __syncthreads_or(zmask != 0);          // (also orders the resets above)
+        const uint32_t nTok = min(RP_TOKENS, T - tS);
+        if (!anyMatch) {
+            // ---- literals only: the output is the c stream itself ---------------------------------------------------
+            if (cur + nTok > kBlockBytes) { if (tid == 0) sm.bad = 1; break; }
+            for (uint32_t j = tid; j < nTok; j += DEC_THREADS) ring[(cur + j) & RP_MASK] = __ldcg(cs + tS + j);
+            __syncthreads();
+            const uint32_t newCur = cur + nTok, fe = newCur & ~3u;
+            for (uint32_t w = (flushed >> 2) + tid; w < (fe >> 2); w += DEC_THREADS)
+                o32[w] = reinterpret_cast<const uint32_t *>(ring)[w & (RP_MASK >> 2)];
+            flushed = fe; cur = newCur; tS += nTok;
+            __syncthreads();                                         // the ring is rewritten by the next batch
+            continue;
+        }
+        // match ranks: exclusive scan of the per-thread match counts
+        const uint32_t mine = (uint32_t)__popc(zmask);
+        uint32_t inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
             if (lane >= d) inc += v;
         }
-        if (lane == 31) sm.warpTot[warp] = inc;
+        if (lane == 31) sm.warpA[warp] = inc;
         __syncthreads();
-        uint32_t rank = mBase + inc - mine, tot = 0;
+        uint32_t rank = mBase + inc - mine;
 #pragma unroll
-        for (int w = 0; w < DEC_THREADS / 32; w++) { const uint32_t v = sm.warpTot[w]; if (w < warp) rank += v; tot += v; }
-        mBase += tot;
-        unsigned long long lits = 0;
-        if (nvalid) lits = __ldcg(reinterpret_cast<const unsigned long long *>(cs + tb));   // 8-byte aligned, buffer is padded
+        for (int w = 0; w < DEC_WARPS; w++) if (w < warp) rank += sm.warpA[w];
+        uint32_t Lp[RP_PER / 2], len1sum = 0;                        // the eight lengths / markers, two per register
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            uint32_t L = DEC_TOK_NONE, P = 0;
+        for (int i = 0; i < RP_PER; i++) {
+            uint32_t l = RP_NONE, P = 0;
             if ((uint32_t)i < nvalid) {
-                L = 0;
+                l = 0;
                 if ((zmask >> i) & 1u) {
                     const uint32_t m = rank + (uint32_t)__popc(zmask & ((1u << i) - 1u));
-                    if (m >= Pc) L = DEC_TOK_STOP;                   // mc:2337-2340: "Fatal Error", stop before this token
-                    else if (m >= nL) L = DEC_TOK_BAD;               // its Golomb code ran past the stream
+                    if (m >= Pc) l = RP_STOP;                        // mc:2337-2340: "Fatal Error", stop before this token
+                    else if (m >= nL) l = RP_BADTOK;                 // its Golomb code ran past the stream
                     else {
-                        L = __ldcg(lv + m);
+                        l = __ldcg(lv + m);
                         const uint32_t bp = kPBits * m, by = bp >> 3;   // decombine_bits, mc:1315-1338
                         const uint32_t raw = (uint32_t)__ldcg(pk + by) | ((uint32_t)__ldcg(pk + by + 1) << 8) |
                                              ((uint32_t)__ldcg(pk + by + 2) << 16);
                         P = (raw >> (bp & 7)) & 0x7FFu;
-                        if (L > (uint32_t)kMaxLen) L = DEC_TOK_BAD;
+                        if (l > (uint32_t)kMaxLen || P == 0) l = RP_BADTOK;
                     }
                 }
             }
-            sm.tokL[8 * tid + i] = (uint16_t)L;
-            sm.tokP[8 * tid + i] = (uint16_t)P;
-            sm.tokC[8 * tid + i] = (uint8_t)(lits >> (8 * i));
+            if (l == RP_STOP) atomicMin(&sm.firstStop, (uint32_t)RP_PER * tid + i);
+            if (l == RP_BADTOK) atomicMin(&sm.firstBad, (uint32_t)RP_PER * tid + i);
+            if (i & 1) Lp[i >> 1] |= l << 16; else Lp[i >> 1] = l;
+            sm.tokL[RP_PER * tid + i] = (uint16_t)l;
+            sm.tokP[RP_PER * tid + i] = (uint16_t)P;
+            len1sum += l < RP_NONE ? l + 1 : 0u;
         }
-        __syncthreads();
-        // ---- replay ---------------------------------------------------------------------------------------
-        if (warp == 0) {
-            const uint32_t nTok = min((uint32_t)DEC_SUPER, T - tS);
-            bool stop = false;
-            for (uint32_t bb = 0; bb < nTok && !stop && !bad; bb += 32) {
-                uint32_t l = sm.tokL[bb + lane];
-                const uint32_t p = sm.tokP[bb + lane], lit = sm.tokC[bb + lane];
-                bool valid = l != DEC_TOK_NONE;
-                const uint32_t special = __ballot_sync(0xFFFFFFFFu, l == DEC_TOK_STOP || l == DEC_TOK_BAD);
-                if (special) {
-                    const int first = __ffs(special) - 1;
-                    if (__shfl_sync(0xFFFFFFFFu, l, first) == DEC_TOK_BAD) { bad = true; break; }
-                    valid = valid && lane < first;
-                    stop = true;
-                }
-                if (!valid) l = 0;
-                const uint32_t len1 = valid ? l + 1 : 0;
-                uint32_t sc = len1;
+        // output positions: exclusive scan of len + 1 (tokens behind a stop / bad marker never count: cut below)
+        uint32_t incB = len1sum;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, sc, d);
-                    if (lane >= d) sc += v;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, sc, 31);
-                const uint32_t pos = cur + sc - len1;
-                const bool badLane = valid && ((l && (p == 0 || p > pos)) || (unsigned long long)pos + l + 1 > kBlockBytes);
-                if (__any_sync(0xFFFFFFFFu, badLane)) { bad = true; break; }
-                // a token is independent when all its source bytes were produced before this trip
-                const bool dep = valid && l && (pos - p + l > cur);
-                if (valid) {
-                    if (!dep) for (uint32_t k = 0; k < l; k++) ring[(pos + k) & RM] = ring[(pos - p + k) & RM];   // mc:1730-1732
-                    ring[(pos + l) & RM] = (uint8_t)lit;                                                         // mc:1734
-                }
-                __syncwarp();
-                uint32_t depMask = __ballot_sync(0xFFFFFFFFu, dep);
-                while (depMask) {                                    // in order: each may read what the previous wrote
-                    const int d = __ffs(depMask) - 1;
-                    depMask &= depMask - 1;
-                    const uint32_t pd = __shfl_sync(0xFFFFFFFFu, pos, d), ld = __shfl_sync(0xFFFFFFFFu, l, d),
-                                   sd = __shfl_sync(0xFFFFFFFFu, p, d);
-                    // the source window [pd-sd, pd) is final; an overlapping copy repeats it with period sd
-                    for (uint32_t k = lane; k < ld; k += 32) {
-                        const uint32_t off = sd >= ld ? k : k % sd;
-                        ring[(pd + k) & RM] = ring[(pd - sd + off) & RM];
-                    }
-                    __syncwarp();
-                }
-                // ---- flush the finished whole words to HBM ---------------------------------------------
-                const uint32_t newCur = cur + total;
-                const uint32_t fe = newCur & ~3u;
-                for (uint32_t w = (flushed >> 2) + lane; w < (fe >> 2); w += 32)
-                    o32[w] = reinterpret_cast<const uint32_t *>(ring)[w & (RM >> 2)];
-                flushed = fe;
-                cur = newCur;
-                __syncwarp();
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incB, d);
+            if (lane >= d) incB += v;
+        }
+        if (lane == 31) sm.warpB[warp] = incB;
+        __syncthreads();                                             // warpB, firstStop, firstBad are complete
+        uint32_t pos = incB - len1sum;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS; w++) if (w < warp) pos += sm.warpB[w];
+        // how many tokens this batch takes: up to the first stop / malformed token, and what fits RP_BYTES of output
+        const uint32_t firstStop = sm.firstStop, firstBad = sm.firstBad;
+        const uint32_t limitTok = min(min(nTok, firstStop), firstBad);
+        {
+            uint32_t p = pos;
+#pragma unroll
+            for (int i = 0; i < RP_PER; i++) {
+                const uint32_t idx = (uint32_t)RP_PER * tid + i;
+                const uint32_t l = (Lp[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+                const uint32_t l1 = l < RP_NONE ? l + 1 : 0u;
+                sm.tokPos[idx] = (uint16_t)min(p, 0xFFFFu);
+                if (idx < limitTok && p + l1 > RP_BYTES) atomicMin(&sm.nTake, idx);
+                p += l1;
             }
-            if (lane == 0 && (stop || bad)) sm.fin = 1;
         }
         __syncthreads();
-        if (sm.fin) break;
+        const uint32_t nTake = min(limitTok, sm.nTake);
+        if (nTake == 0) {
+            // the batch opens with the stop (the block ends here) or with a malformed token
+            if (firstBad == 0 && tid == 0) sm.bad = 1;
+            break;
+        }
+        // bytes and matches of the taken tokens; distances are checked against the bytes decoded so far
+        {
+            uint32_t myMat = 0;
+            bool badLane = false;
+#pragma unroll
+            for (int i = 0; i < RP_PER; i++) {
+                const uint32_t idx = (uint32_t)RP_PER * tid + i;
+                if (idx < nTake) {
+                    const uint32_t l = (Lp[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+                    if ((zmask >> i) & 1u) {
+                        myMat++;
+                        if (sm.tokP[idx] > cur + sm.tokPos[idx]) badLane = true;     // reaches before the block's first byte
+                    }
+                    if (idx == nTake - 1) sm.takeBytes = sm.tokPos[idx] + l + 1;
+                }
+            }
+            if (myMat) atomicAdd(&sm.takeMatches, myMat);
+            if (badLane) sm.bad = 1;
+        }
+        __syncthreads();
+        const uint32_t B = sm.takeBytes;
+        if (sm.bad) break;
+        if (cur + B > kBlockBytes) { if (tid == 0) sm.bad = 1; break; }
+        // ---- per byte: where it comes from.  Literals go to the ring at once and point at themselves ------------
+        for (uint32_t j = tid; j < nTake; j += DEC_THREADS) {
+            const uint32_t l = sm.tokL[j], p = sm.tokP[j], at = sm.tokPos[j];
+            for (uint32_t k = 0; k < l; k++) sm.src[at + k] = (int16_t)((int)(at + k) - (int)p);     // mc:1730-1732
+            sm.src[at + l] = (int16_t)(at + l);
+            ring[(cur + at + l) & RP_MASK] = __ldcg(cs + tS + j);                                    // mc:1734
+        }
+        __syncthreads();
+        // ---- pointer doubling: a byte that copies a copy points at that copy's source, until every pointer leaves
+        // the batch (negative) or rests on a literal ----------------------------------------------------------------
+        for (;;) {
+            bool changed = false;
+            for (uint32_t q = tid; q < B; q += DEC_THREADS) {
+                const int s = sm.src[q];
+                if (s >= 0 && s != (int)q) {
+                    const int s2 = sm.src[s];
+                    if (s2 != s) { sm.src[q] = (int16_t)s2; changed = true; }
+                }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        // ---- fetch: sources are final (earlier batches, or literals of this one) -----------------------------------
+        for (uint32_t q = tid; q < B; q += DEC_THREADS) {
+            const int s = sm.src[q];
+            if (s != (int)q) ring[(cur + q) & RP_MASK] = ring[(uint32_t)((int)cur + s) & RP_MASK];
+        }
+        __syncthreads();
+        // ---- flush the finished whole words to HBM -------------------------------------------------------------------
+        const uint32_t newCur = cur + B, fe = newCur & ~3u;
+        for (uint32_t w = (flushed >> 2) + tid; w < (fe >> 2); w += DEC_THREADS)
+            o32[w] = reinterpret_cast<const uint32_t *>(ring)[w & (RP_MASK >> 2)];
+        flushed = fe; cur = newCur;
+        mBase += sm.takeMatches;
+        tS += nTake;
+        if (nTake < nTok && nTake == firstStop) break;               // the next token is the stop: the block ends here
+        if (nTake < nTok && nTake == firstBad) { if (tid == 0) sm.bad = 1; break; }
+        __syncthreads();                                             // ring / token arrays are rewritten by the next batch
     }
-    if (warp == 0) {
-        if (!bad) for (uint32_t i = flushed + lane; i < cur; i += 32) o[i] = ring[i & RM];
-        if (lane == 0) outLen[b] = bad ? DEC_BAD : cur;
-    }
+    __syncthreads();
+    const bool bad = sm.bad != 0;
+    if (!bad) for (uint32_t i = flushed + tid; i < cur; i += DEC_THREADS) o[i] = ring[i & RP_MASK];
+    if (tid == 0) { outLen[b] = bad ? DEC_BAD : cur; meta->nL = nL; }
 }
 
-void decode_init() {}
+void decode_init()
+{
+    cudaFuncSetAttribute(k_dec_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReplaySmem));
+}
 
 int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out,
                   uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st)
 {
     // the reference decodes into zero-initialised buffers (mc:2270,2282,2291,2305)
     cudaMemsetAsync(d_scratch, 0, scratchPerBlock * nBlocks, st);
-    k_decode<<<nBlocks, DEC_THREADS, 0, st>>>(d_file, d_recOff, d_out, d_outLen, d_scratch, scratchPerBlock);
-    return 1;
+    k_dec_parse<<<(nBlocks + 127) / 128, 128, 0, st>>>(d_file, d_recOff, nBlocks, d_scratch, scratchPerBlock);
+    k_dec_sections<<<dim3(4, nBlocks), DEC_THREADS, 0, st>>>(d_file, d_recOff, d_scratch, scratchPerBlock);
+    k_dec_replay<<<nBlocks, DEC_THREADS, sizeof(ReplaySmem), st>>>(d_out, d_outLen, d_scratch, scratchPerBlock);
+    return 3;
 }
 
 } // namespace fcx

@@ -23,7 +23,7 @@ using namespace fcx;
 namespace {
 
 constexpr uint32_t kMaxPipeBatches = 256;       // batches per device and call
-constexpr uint32_t kDecBatchBlocks = 128;       // blocks per decode batch
+constexpr uint32_t kDecBatchBlocks = 256;       // blocks per decode batch
 constexpr uint32_t kDecRing = 3;                // decode batches in flight per device (device output slots)
 
 struct DevSlot {

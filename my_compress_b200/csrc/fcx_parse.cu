@@ -13,9 +13,9 @@
 //   k_parse_emit    every tile walks its part of the chain ONCE: counts its tokens, matches and
 //                   Golomb bits, publishes them, packs c bytes, flag bits, 11-bit distances and
 //                   Golomb codes into shared memory, learns the rank of its first token from the
-//                   tiles before it (decoupled look-back over one 64-bit status word per tile --
-//                   the device-wide scan of the parse -- while the packing is under way), and
-//                   copies the packed bits to their final bit positions
+//                   counts the tiles before it have published (one 64-bit status word per tile:
+//                   the device-wide scan of the parse, overlapped with the packing), and copies
+//                   the packed bits to their final bit positions
 // Inside a tile the chain is resolved by a three-level jump table:
 //   J1[i] = first chain position at or beyond the end of i's 16-position mini-tile
 //   J2[i] = first chain position at or beyond the end of i's 256-position mid-tile
@@ -183,9 +183,9 @@ struct EmitSmem {
     unsigned long long base;              // look-back result: packed exclusive ranks of the tile's first token
 };
 
-// One status word per tile (ws.tileState, zeroed per launch): status << 62 | Golomb bits << 40 | matches << 21 | tokens.
-// Fields are sums over at most one block (tokens <= 2^20, matches <= 2^18, Golomb bits < 2^20), so packed words add
-// without carries between fields.  status 1 = the tile's own counts, 2 = counts of the tile and of all tiles before it.
+// One status word per tile (ws.tileState, zeroed per launch): ready << 62 | Golomb bits << 40 | matches << 21 | tokens.
+// Sums over a block stay inside the fields (tokens <= 2^20, matches <= 2^18, Golomb bits < 2^20), so packed words add
+// without carries between fields.
 constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
 __device__ __forceinline__ unsigned long long ts_pack(uint32_t tok, uint32_t mat, uint32_t gb)
 {
@@ -205,49 +205,49 @@ __device__ __forceinline__ unsigned long long ts_load(const unsigned long long *
     return v;
 }
 
-// Decoupled look-back by one warp (all 32 lanes): sum of the counts of tiles 0..tile-1 of this block.  Lane j looks at
-// tile t-j; the nearest word that already holds a prefix ends the walk.  Tiles of a block have consecutive CTA numbers
-// (blockIdx.x runs fastest) and a CTA only ever waits for lower-numbered ones, which were dispatched before it.
+// Ranks by one warp (all 32 lanes): sum of the counts of tiles 0..tile-1 of this block.  Every tile publishes its own
+// counts as soon as it knows them (before it packs its tokens), so by the time a tile asks, the words of the tiles
+// before it are usually all there: lane j reads words j, j + 32, ... (at most eight, all loads in flight at once) and
+// only spins on the ones not yet written.  Tiles of a block have consecutive CTA numbers (blockIdx.x runs fastest)
+// and a CTA only ever waits for lower-numbered ones, which were dispatched before it.
 __device__ __forceinline__ unsigned long long tile_lookback(const unsigned long long *row, int tile, int lane)
 {
-    unsigned long long acc = 0;
-    for (int t = tile - 1; t >= 0; t -= 32) {
-        const int idx = t - lane;
-        unsigned long long v;
-        do {
-            v = idx >= 0 ? ts_load(row + idx) : (2ull << 62);           // before tile 0: an empty prefix
-        } while (__any_sync(0xFFFFFFFFu, (v >> 62) == 0));
-        const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-        const int first = incl ? __ffs(incl) - 1 : 32;
-        unsigned long long c = lane <= first ? (v & TS_MASK) : 0ull;
+    static_assert(kParseTilesPerBlock == 256, "eight words per lane");
+    unsigned long long v[8];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-        acc += c;
-        if (incl) break;
+    for (int k = 0; k < 8; k++) { const int j = lane + 32 * k; v[k] = j < tile ? ts_load(row + j) : (1ull << 62); }
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int j = lane + 32 * k;
+        while ((v[k] >> 62) == 0) v[k] = ts_load(row + j);
+        if (j < tile) acc += v[k] & TS_MASK;
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
     return acc;
 }
 
-// publishes the tile's counts, waits for the ranks of its first token, publishes the running totals; the last tile
-// of a block also writes the block's meta words.  Called by warp 0 (all lanes); returns the packed exclusive ranks.
+// waits for the ranks of the tile's first token (its own counts were published earlier by publish_counts); the last
+// tile of a block also writes the block's meta words.  Called by warp 0 (all lanes); returns the packed exclusive ranks.
+__device__ __forceinline__ void publish_counts(const Ws &ws, int b, int tile, unsigned long long mine)
+{
+    ts_store(ws.tileState + (size_t)b * kParseTilesPerBlock + tile, (1ull << 62) | mine);
+}
 __device__ __forceinline__ unsigned long long tile_ranks(const Ws &ws, int b, int tile, int nTiles, int lane, unsigned long long mine)
 {
-    unsigned long long *row = ws.tileState + (size_t)b * kParseTilesPerBlock;
-    if (tile > 0 && lane == 0) ts_store(row + tile, (1ull << 62) | mine);
+    const unsigned long long *row = ws.tileState + (size_t)b * kParseTilesPerBlock;
     const unsigned long long before = tile_lookback(row, tile, lane);
-    if (lane == 0) {
+    if (lane == 0 && tile == nTiles - 1) {
         const unsigned long long incl = before + mine;
-        ts_store(row + tile, (2ull << 62) | incl);
-        if (tile == nTiles - 1) {
-            const uint32_t ta = ts_tok(incl), tc = ts_mat(incl), tg = ts_gb(incl);
-            const uint32_t G = (tg + 31) >> 5;                        // mc:295-302: last partial word is flushed
-            uint32_t *m = ws.meta + (size_t)b * M_WORDS;
-            m[M_T] = ta; m[M_PC] = tc; m[M_G] = G; m[M_GBITS] = tg;
-            m[M_S0] = (ta + 7) >> 3;                                  // mc:2077-2078
-            m[M_S1] = ta;
-            m[M_S2] = (kPBits * tc) / 8 + 1;                          // mc:2193: one spare byte when divisible
-            m[M_S3] = 4 * G;                                          // mc:2230-2236: words viewed as bytes
-        }
+        const uint32_t ta = ts_tok(incl), tc = ts_mat(incl), tg = ts_gb(incl);
+        const uint32_t G = (tg + 31) >> 5;                        // mc:295-302: last partial word is flushed
+        uint32_t *m = ws.meta + (size_t)b * M_WORDS;
+        m[M_T] = ta; m[M_PC] = tc; m[M_G] = G; m[M_GBITS] = tg;
+        m[M_S0] = (ta + 7) >> 3;                                  // mc:2077-2078
+        m[M_S1] = ta;
+        m[M_S2] = (kPBits * tc) / 8 + 1;                          // mc:2193: one spare byte when divisible
+        m[M_S3] = 4 * G;                                          // mc:2230-2236: words viewed as bytes
     }
     return before;
 }
@@ -309,6 +309,7 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
             }
             reinterpret_cast<uint4 *>(sm.xs)[tid] = q;
         }
+        if (tid == 0) publish_counts(ws, b, tile, ts_pack(tileTok, 0, 0));
         if (warp == 0) {
             const unsigned long long r = tile_ranks(ws, b, tile, nTiles, lane, ts_pack(tileTok, 0, 0));
             if (lane == 0) sm.base = r;
@@ -386,11 +387,9 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     const uint32_t exP = baseP + incP - packed;
     uint32_t tokIdx = exP & 0xFFFF, matIdx = exP >> 16, gOff = baseG + incG - myGb;
     const uint32_t tileTok = tileP & 0xFFFF, tileMat = tileP >> 16;
-    // the tile's counts are known: tell the tiles behind this one before the packing starts (status 1; tile 0 has
-    // nothing to wait for and publishes its prefix right away)
-    unsigned long long *row = ws.tileState + (size_t)b * kParseTilesPerBlock;
+    // the tile's counts are known: tell the tiles behind this one before the packing starts
     const unsigned long long mine = ts_pack(tileTok, tileMat, tileG);
-    if (tid == 0 && tile > 0) ts_store(row + tile, (1ull << 62) | mine);
+    if (tid == 0) publish_counts(ws, b, tile, mine);
 
     // A thread's tokens have consecutive ranks, so its flag bits (<= 16) and packed distances
     // (<= 5 x 11 bits) are contiguous: gather them in registers and merge once, instead of one

@@ -1,49 +1,40 @@
 #!/usr/bin/env python
 """Per-source-line instruction / stall-sample totals of one kernel from an ncu report:
-    python tools/ncu_lines.py gpurun_out/x.ncu-rep [top]
+    python tools/ncu_lines.py gpurun_out/x.ncu-rep [top] [kernel-regex]
 Uses `ncu --page source --csv --print-source cuda,sass` (needs -lineinfo builds and --import-source on)."""
 import csv
 import io
 import re
 import subprocess
 import sys
-from collections import defaultdict
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+if len(sys.argv) > 3:
+    cmd += ["-k", "regex:" + sys.argv[3]]
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-# layout: blocks of [cuda line row] followed by its sass rows; find the header row of metrics
 hdr = None
-agg = defaultdict(lambda: [0, 0, 0, ""])      # line -> [inst, thread inst, samples, text]
-cur = None
+agg = {}
 for r in rows:
     if not r:
         continue
-    if r[0] in ("Address", "Line No") or "Instructions Executed" in r:
+    if r[0] == "Line No":
         hdr = r
+        i_inst, i_thr, i_smp = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
         continue
-    if hdr is None:
-        continue
-    try:
-        i_inst = hdr.index("Instructions Executed")
-        i_thr = hdr.index("Thread Instructions Executed")
-        i_smp = hdr.index("# Samples")
-    except ValueError:
-        continue
-    key = r[0]
-    if re.fullmatch(r"\d+", key):             # a CUDA source line row
-        cur = int(key)
-        agg[cur][3] = r[1]
-        continue
-    if cur is None or len(r) <= max(i_inst, i_thr, i_smp):
+    if hdr is None or not re.fullmatch(r"\d+", r[0]) or len(r) <= i_thr:
         continue
     try:
-        agg[cur][0] += int(float(r[i_inst] or 0))
-        agg[cur][1] += int(float(r[i_thr] or 0))
-        agg[cur][2] += int(float(r[i_smp] or 0))
+        v = [int(float(r[i_inst] or 0)), int(float(r[i_thr] or 0)), int(float(r[i_smp] or 0)), r[1]]
     except ValueError:
-        pass
+        continue
+    ln = int(r[0])
+    if ln in agg:
+        agg[ln][0] += v[0]; agg[ln][1] += v[1]; agg[ln][2] += v[2]
+    else:
+        agg[ln] = v
 tot_i = sum(v[0] for v in agg.values()) or 1
 tot_s = sum(v[2] for v in agg.values()) or 1
 print("total warp-instructions %d, samples %d" % (tot_i, tot_s))
