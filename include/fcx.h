@@ -75,6 +75,16 @@ int fcx_decompress_lz77(const uint8_t *file, uint64_t nbytes, uint8_t *out, uint
 int fcx_decompress_records_lz77(const uint8_t *records, uint64_t nbytes, uint32_t n_blocks, uint8_t *out,
                                 uint64_t out_cap, uint64_t *out_n, uint32_t device_mask);
 
+/* The lz78 twins: "-c <anything but lz77>" of the reference CLI writes an FCX8 container (mc:4040-4043, 4080-4081)
+ * with my_compress_file_lz78 (mc:3127, called at mc:4106) per block.  Same bytes as the reference; payloads can be
+ * larger than the input (fcx_compress_bound_lz78).  fcx_decompress_lz77 / fcx_decompress_block_lz78 read them back
+ * (my_decompress_file_lz78, mc:3478, called at mc:4189), including the unconditional drop of a trailing 0x00
+ * (mc:3701-3703). */
+uint64_t fcx_compress_bound_lz78(uint64_t n);
+int fcx_compress_block_lz78(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t out_cap, uint32_t *out_n);
+int fcx_compress_lz78(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_n, uint32_t device_mask);
+int fcx_decompress_block_lz78(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap, uint32_t *out_n);
+
 /* Host buffers: any memory works, page-locked memory lets the copies run at full PCIe speed and overlap the
  * kernels (the reference's fread/fwrite buffers, mc:4073 and mc:4088, are what these replace).  NULL on
  * failure.  Pageable buffers are copied through the driver's staging area: correct, but slower. */

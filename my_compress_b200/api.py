@@ -34,7 +34,8 @@ EXPORTS = [
     "fcx_last_error", "fcx_device_count", "fcx_compress_bound", "fcx_compress_block_lz77", "fcx_compress_lz77",
     "fcx_decompress_block_lz77", "fcx_decompress_lz77", "fcx_ctx_create", "fcx_ctx_destroy", "fcx_ctx_set_stream",
     "fcx_compress_lz77_device", "fcx_decompress_lz77_device", "fcx_ctx_finish", "fcx_ctx_launch_count", "fcx_ctx_stats", "fcx_ctx_enable_timing",
-    "fcx_ctx_stage_times", "fcx_compress_records_lz77", "fcx_decompress_records_lz77", "fcx_host_alloc", "fcx_host_free",
+    "fcx_ctx_stage_times", "fcx_compress_bound_lz78", "fcx_compress_block_lz78", "fcx_compress_lz78", "fcx_decompress_block_lz78",
+    "fcx_compress_records_lz77", "fcx_decompress_records_lz77", "fcx_host_alloc", "fcx_host_free",
     "fcx_ctx_debug_guards", "fcx_probe_match", "fcx_probe_match_auto", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
 ]
 
@@ -55,6 +56,11 @@ def lib():
     L.fcx_compress_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
     L.fcx_compress_records_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
     L.fcx_decompress_records_lz77.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.fcx_compress_bound_lz78.restype = C.c_uint64
+    L.fcx_compress_bound_lz78.argtypes = [C.c_uint64]
+    L.fcx_compress_block_lz78.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.fcx_compress_lz78.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.fcx_decompress_block_lz78.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.fcx_host_alloc.restype = C.c_void_p
     L.fcx_host_alloc.argtypes = [C.c_uint64]
     L.fcx_host_free.restype = None
@@ -160,6 +166,36 @@ def decompress_records(records, n_blocks, n_gpus=1):
     out = np.empty(max(1, n_blocks) * (BLOCK_BYTES + 8), np.uint8)
     n = C.c_uint64(0)
     _check(lib().fcx_decompress_records_lz77(x.ctypes.data, len(x), int(n_blocks), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+# ---- lz78 / FCX8 twins (mc:3127, mc:3478; "-c <anything but lz77>" of the reference CLI) -------------------
+
+def my_compress_file_lz78(data):
+    """One block (<= 1 MiB) -> FCX8 payload bytes; same bytes as mc:3127 writes to pOut."""
+    x = _host_u8(data)
+    out = np.empty(int(lib().fcx_compress_bound_lz78(len(x))), np.uint8)
+    n = C.c_uint32(0)
+    _check(lib().fcx_compress_block_lz78(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def my_decompress_file_lz78(payload):
+    """One FCX8 block payload -> the bytes mc:3478 writes to its FILE* (a trailing 0x00 dropped, App. B2)."""
+    x = _host_u8(payload)
+    out = np.empty(BLOCK_BYTES + 8, np.uint8)
+    n = C.c_uint32(0)
+    _check(lib().fcx_decompress_block_lz78(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def compress_lz78(data, n_gpus=1):
+    """``./my_compress -i in -o out -c lz78`` on a buffer: FCX8 container bytes."""
+    x = _host_u8(data)
+    out = np.empty(int(lib().fcx_compress_bound_lz78(len(x))), np.uint8)
+    src = x if len(x) else np.zeros(1, np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_compress_lz78(src.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
     return out[: n.value].tobytes()
 
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfcx.so")
-SOURCES = ["fcx_api.cu", "fcx_host.cu", "fcx_match.cu", "fcx_parse.cu", "fcx_huff.cu", "fcx_decode.cu"]
+SOURCES = ["fcx_api.cu", "fcx_host.cu", "fcx_match.cu", "fcx_parse.cu", "fcx_huff.cu", "fcx_decode.cu", "fcx_lz78.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

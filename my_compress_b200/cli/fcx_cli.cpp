@@ -8,7 +8,9 @@
 // A piece is 256 MiB of input (256 blocks; the reference's piece is one block).  A reader thread fills one
 // page-locked buffer while the GPU works on the other and a writer thread drains the previous result, so disk,
 // PCIe and kernels overlap; the bytes written are identical to the reference's.  Unlike the reference it prints
-// nothing but errors, and "-c <anything else>" (lz78) is refused.
+// nothing but errors.  "-c <anything else>" means lz78 as in the reference (mc:4040-4043): FCX8 files go through
+// fcx_compress_lz78 / fcx_decompress_lz77 in one piece (the lz78 tokenizer is a sequential walk per block; there
+// is nothing for a file pipeline to overlap with).
 #include "../../include/fcx.h"
 
 #include <getopt.h>
@@ -122,10 +124,7 @@ int main(int argc, char **argv)
         else if (opt == 'c' && optarg) { algo = optarg; compress = true; }
         else if (opt == 'g' && optarg) gpus = atoi(optarg);
     }
-    if (compress && strncmp(algo.c_str(), "lz77", 4) != 0) {          // mc:4040-4043: anything else means lz78
-        fprintf(stderr, "only -c lz77 is on this path (lz78 containers are out of scope)\n");
-        return 255;
-    }
+    const bool lz78 = compress && strncmp(algo.c_str(), "lz77", 4) != 0;     // mc:4040-4043: anything else means lz78
     const int nd = fcx_device_count();
     if (nd == 0) { fprintf(stderr, "fcx: no CUDA device (this path has no CPU fallback)\n"); return 255; }
     gpus = gpus < 1 ? 1 : gpus > nd ? nd : gpus;
@@ -134,6 +133,35 @@ int main(int argc, char **argv)
     if (!fin) { fprintf(stderr, "open: %s Fail!!\n", in.c_str()); return 255; }       // mc:4058-4062
     FILE *fout = fopen(out.c_str(), "wb");
     if (!fout) { fprintf(stderr, "open: %s Fail!!\n", out.c_str()); fclose(fin); return 255; }
+    // FCX8: whole file in one call (compress: -c lz78; decompress: magic byte '8', mc:4153-4164)
+    bool whole = lz78;
+    if (!compress) {
+        uint8_t magic[4] = {0, 0, 0, 0};
+        const size_t k = fread(magic, 1, 4, fin);
+        whole = k == 4 && memcmp(magic, "FCX8", 4) == 0;
+        fseek(fin, 0, SEEK_SET);
+    }
+    if (whole) {
+        fseek(fin, 0, SEEK_END);
+        const long sz = ftell(fin);
+        fseek(fin, 0, SEEK_SET);
+        const uint64_t n = sz > 0 ? (uint64_t)sz : 0;
+        uint16_t blocks = 0;
+        uint8_t *src = static_cast<uint8_t *>(fcx_host_alloc(n + 16));
+        if (!src || fread(src, 1, n, fin) != n) { fprintf(stderr, "read: %s Fail!!\n", in.c_str()); return 255; }
+        if (!compress && n >= FCX_HEADER_BYTES) memcpy(&blocks, src + 8, 2);
+        const uint64_t cap = compress ? fcx_compress_bound_lz78(n) : (uint64_t)(blocks ? blocks : 1) * (FCX_BLOCK_BYTES + 8);
+        uint8_t *dst = static_cast<uint8_t *>(fcx_host_alloc(cap));
+        uint64_t produced = 0;
+        const int rc = !dst ? FCX_ERR_CUDA
+                            : compress ? fcx_compress_lz78(src, n, dst, cap, &produced, mask) : fcx_decompress_lz77(src, n, dst, cap, &produced, mask);
+        bool ok = rc == FCX_OK && (produced == 0 || fwrite(dst, 1, produced, fout) == produced);
+        if (rc != FCX_OK) fprintf(stderr, "fcx error %d: %s\n", rc, fcx_last_error());
+        fcx_host_free(src); fcx_host_free(dst);
+        fclose(fin);
+        if (fclose(fout) != 0) ok = false;
+        return ok ? 0 : 255;
+    }
 
     Pipe p;
     const uint64_t inCap = compress ? kPieceBytes : fcx_compress_bound(kPieceBytes);

@@ -178,6 +178,7 @@ extern "C" void fcx_ctx_destroy(fcx_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    lz78_release(c);
     for (void *p : c->allocs) cudaFree(p);
     if (c->hostStatus) cudaFreeHost(c->hostStatus);
     delete c;

@@ -510,19 +510,25 @@ int scan_records(const uint8_t *file, uint64_t nbytes, uint64_t pos, uint64_t co
 
 } // namespace
 
+namespace {
+int decompress_lz78_host(const uint8_t *file, const std::vector<uint64_t> &rec, uint64_t recEnd, uint8_t *out, uint64_t outCap,
+                         uint64_t *outN, uint32_t mask);
+}
+
 extern "C" int fcx_decompress_lz77(const uint8_t *file, uint64_t nbytes, uint8_t *out, uint64_t outCap, uint64_t *outN,
                                    uint32_t deviceMask)
 {
     if (!file || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");
     if (nbytes < 10) return fail(FCX_ERR_FORMAT, "shorter than the 10-byte header");               // mc:4139-4144
     if (memcmp(file, "FCX", 3) != 0) return fail(FCX_ERR_FORMAT, "not an FCX container");          // mc:4146-4152
-    if (file[3] != '7') return fail(FCX_ERR_UNSUPPORTED, "FCX8 (lz78) containers are not on this path");
+    if (file[3] != '7' && file[3] != '8') return fail(FCX_ERR_FORMAT, "not an FCX7 / FCX8 container");   // mc:4153-4164
     if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
     uint16_t nb16; memcpy(&nb16, file + 8, 2);
     std::vector<uint64_t> rec;
     uint64_t end = 10;
     int rc = scan_records(file, nbytes, 10, nb16, rec, end);
     if (rc) return rc;
+    if (file[3] == '8') return decompress_lz78_host(file, rec, end, out, outCap, outN, deviceMask);   // mc:4189
     return decompress_host(file, rec, end, out, outCap, outN, deviceMask);
 }
 
@@ -551,6 +557,132 @@ extern "C" int fcx_decompress_block_lz77(const uint8_t *payload, uint32_t nbytes
     int rc = decompress_host(rec.data(), off, rec.size(), out, outCap, &got, 1);
     if (rc) return rc;
     *outN = (uint32_t)got;
+    return FCX_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// FCX8 (lz78): "-c <anything but lz77>" of the reference CLI (mc:4040-4043, mc:4106)
+// -----------------------------------------------------------------------------------------
+// The tokenizer walks every block sequentially (one thread per block, see fcx_lz78.cu), so the device time
+// dwarfs the copies: one upload, the kernels, one download, on the first device of the mask.
+namespace {
+int compress_lz78_host(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, uint64_t *outN, uint32_t mask, bool withHeader)
+{
+    if (!out || !outN || (!in && n)) return fail(FCX_ERR_ARG, "null pointer");
+    const int nd = fcx_device_count();
+    if (nd == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+    const std::vector<int> devs = devices_of(mask, nd);
+    if (devs.empty()) return fail(FCX_ERR_ARG, "device_mask selects no visible device");
+    DevSlot &s = g_slots[devs[0]];
+    std::lock_guard<std::mutex> lk(s.mu);
+    const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
+    // lz78 payloads can exceed the lz77 bound (32-bit tree nodes, group codes): the reference's own buffer is 2 MiB per block
+    const uint64_t bound = 10 + nBlocks * (4 + (5ull << 19) + (1ull << 20) + 4096) + 64;
+    int rc = slot_prepare_compress(s, devs[0], std::max<uint64_t>(n, 16), bound, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nBlocks, 1), 256));
+    if (rc) return rc;
+    if (n) CK(cudaMemcpyAsync(s.dIn, in, n, cudaMemcpyHostToDevice, s.stream));
+    uint64_t got = 0;
+    rc = lz78_compress_device(s.ctx, s.dIn, n, s.dOut, bound, withHeader, n, (uint32_t)nBlocks, &got);
+    if (rc) { cudaStreamSynchronize(s.stream); return rc; }
+    if (got > outCap) return fail(FCX_ERR_CAPACITY, "output buffer smaller than the compressed result");
+    if (got) CK(cudaMemcpyAsync(out, s.dOut, got, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    *outN = got;
+    return FCX_OK;
+}
+} // namespace
+
+namespace {
+// FCX8 records -> bytes: upload, decode in batches of <= 64 blocks (15 MB of scratch each), one download per block
+int decompress_lz78_host(const uint8_t *file, const std::vector<uint64_t> &rec, uint64_t recEnd, uint8_t *out, uint64_t outCap,
+                         uint64_t *outN, uint32_t mask)
+{
+    const int nd = fcx_device_count();
+    if (nd == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+    const std::vector<int> devs = devices_of(mask, nd);
+    if (devs.empty()) return fail(FCX_ERR_ARG, "device_mask selects no visible device");
+    if (rec.empty()) { *outN = 0; return FCX_OK; }
+    DevSlot &s = g_slots[devs[0]];
+    std::lock_guard<std::mutex> lk(s.mu);
+    int rc = slot_streams(s, devs[0]);
+    if (rc) return rc;
+    lz78_decode_init();
+    constexpr uint32_t kBatch = 64;
+    constexpr size_t kStride = (size_t)kBlockBytes + 256;
+    const size_t per = lz78_decode_scratch_per_block();
+    const uint64_t f0 = rec[0] & ~15ull, bytes = recEnd - f0;
+    if ((rc = grow(s.dIn, s.inCap, bytes + 64))) return rc;
+    if ((rc = grow(s.dOut, s.outCap, kBatch * kStride))) return rc;
+    if ((rc = grow(s.decScratch, s.decScratchCap, per * kBatch))) return rc;
+    uint64_t *dRec = nullptr; uint32_t *dLen = nullptr;
+    CK(cudaMalloc(&dRec, sizeof(uint64_t) * kBatch));
+    CK(cudaMalloc(&dLen, sizeof(uint32_t) * kBatch));
+    auto done = [&](int code) { cudaStreamSynchronize(s.stream); cudaFree(dRec); cudaFree(dLen); return code; };
+    if (cudaMemcpyAsync(s.dIn, file + f0, bytes, cudaMemcpyHostToDevice, s.stream) != cudaSuccess ||
+        cudaMemsetAsync(s.dIn + bytes, 0, 32, s.stream) != cudaSuccess) return done(fail(FCX_ERR_CUDA, "H2D copy failed"));
+    uint64_t at = 0;
+    for (size_t b0 = 0; b0 < rec.size(); b0 += kBatch) {
+        const uint32_t nb = (uint32_t)std::min<size_t>(kBatch, rec.size() - b0);
+        uint64_t offs[kBatch];
+        uint32_t lens[kBatch];
+        for (uint32_t i = 0; i < nb; i++) offs[i] = rec[b0 + i] - f0;
+        if (cudaMemcpyAsync(dRec, offs, sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+            return done(fail(FCX_ERR_CUDA, "H2D copy failed"));
+        launch_decode_lz78(s.dIn, dRec, nb, s.dOut, kStride, dLen, s.decScratch, per, s.stream);
+        if (cudaMemcpyAsync(lens, dLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
+            cudaStreamSynchronize(s.stream) != cudaSuccess)
+            return done(fail(FCX_ERR_CUDA, std::string("lz78 decode: ") + cudaGetErrorString(cudaGetLastError())));
+        for (uint32_t i = 0; i < nb; i++) {
+            if (lens[i] == 0xFFFFFFFFu) return done(fail(FCX_ERR_FORMAT, "corrupt block payload"));
+            if (at + lens[i] > outCap) return done(fail(FCX_ERR_CAPACITY, "output buffer too small"));
+            if (lens[i] && cudaMemcpyAsync(out + at, s.dOut + (size_t)i * kStride, lens[i], cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+                return done(fail(FCX_ERR_CUDA, "D2H copy failed"));
+            at += lens[i];
+        }
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) return done(fail(FCX_ERR_CUDA, "D2H copy failed"));
+    }
+    *outN = at;
+    return done(FCX_OK);
+}
+} // namespace
+
+extern "C" int fcx_decompress_block_lz78(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t outCap, uint32_t *outN)
+{
+    if (!payload || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");
+    if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+    std::vector<uint8_t> rec(4 + (size_t)nbytes);
+    memcpy(rec.data(), &nbytes, 4);
+    memcpy(rec.data() + 4, payload, nbytes);
+    std::vector<uint64_t> off(1, 0);
+    uint64_t got = 0;
+    const int rc = decompress_lz78_host(rec.data(), off, rec.size(), out, outCap, &got, 1);
+    if (rc) return rc;
+    *outN = (uint32_t)got;
+    return FCX_OK;
+}
+
+extern "C" uint64_t fcx_compress_bound_lz78(uint64_t n)
+{
+    const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
+    return 10 + nBlocks * (4 + (5ull << 19) + (1ull << 20) + 4096) + 64;
+}
+
+extern "C" int fcx_compress_lz78(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, uint64_t *outN, uint32_t deviceMask)
+{
+    return compress_lz78_host(in, n, out, outCap, outN, deviceMask, true);
+}
+
+extern "C" int fcx_compress_block_lz78(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t outCap, uint32_t *outN)
+{
+    if (!in || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");
+    if (n == 0 || n > kBlockBytes) return fail(FCX_ERR_ARG, "a block holds 1..1048576 bytes (mc:4090)");
+    std::vector<uint8_t> rec((size_t)fcx_compress_bound_lz78(n));
+    uint64_t got = 0;
+    const int rc = compress_lz78_host(in, n, rec.data(), rec.size(), &got, 1, false);
+    if (rc) return rc;
+    if (got < 4 || got - 4 > outCap) return fail(FCX_ERR_CAPACITY, "output buffer smaller than the payload");
+    memcpy(out, rec.data() + 4, got - 4);                  // strip the record's u32 size
+    *outN = (uint32_t)(got - 4);
     return FCX_OK;
 }
 

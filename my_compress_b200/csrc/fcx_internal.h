@@ -26,6 +26,18 @@ int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlo
 size_t decode_scratch_per_block();
 void decode_init();
 
+// fcx_lz78.cu
+} // namespace fcx
+struct fcx_ctx;
+namespace fcx {
+int lz78_compress_device(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out, uint64_t outCap, bool withHeader,
+                         uint64_t hdrBytes, uint32_t hdrBlocks, uint64_t *outBytes);
+void lz78_release(fcx_ctx *c);
+size_t lz78_decode_scratch_per_block();
+void lz78_decode_init();
+int launch_decode_lz78(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out, size_t outStride,
+                       uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st);
+
 // ---- errors (thread-local message behind fcx_last_error) --------------------------------
 int fail(int code, const std::string &msg);
 const std::string &last_error_string();
@@ -62,6 +74,7 @@ struct fcx_ctx {
     uint8_t *decScratch = nullptr;
     uint64_t *decRec = nullptr;
     uint32_t *decLen = nullptr;
+    void *lz78 = nullptr;              // FCX8 workspace (fcx_lz78.cu), allocated on first use
     // last call
     bool pending = false;
     uint64_t lastBytes = 0;

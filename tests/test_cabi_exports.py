@@ -49,8 +49,8 @@ def test_argument_errors(L):
     assert L.fcx_compress_block_lz77(out.ctypes.data, (1 << 20) + 1, out.ctypes.data, 64, C.byref(n32)) == -1
     bad = np.frombuffer(b"NOPE000000000000", np.uint8)
     assert L.fcx_decompress_lz77(bad.ctypes.data, len(bad), out.ctypes.data, 64, C.byref(n), 1) == -5   # mc:4146-4152
-    fcx8 = np.frombuffer(b"FCX8" + bytes(12), np.uint8)
-    assert L.fcx_decompress_lz77(fcx8.ctypes.data, len(fcx8), out.ctypes.data, 64, C.byref(n), 1) == -6
+    fcx9 = np.frombuffer(b"FCX9" + bytes(12), np.uint8)                 # '7' = lz77, '8' = lz78, nothing else (mc:4153-4164)
+    assert L.fcx_decompress_lz77(fcx9.ctypes.data, len(fcx9), out.ctypes.data, 64, C.byref(n), 1) == -5
 
 
 def test_context_batch_limit(L):

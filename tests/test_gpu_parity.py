@@ -15,6 +15,7 @@ from my_compress_b200 import api, datagen
 pytestmark = pytest.mark.gpu
 
 G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+GL = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_lz78.json")))
 
 
 @pytest.fixture(scope="module")
@@ -343,7 +344,14 @@ def test_cli_is_interchangeable_with_the_reference_cli(tmp_path):
     subprocess.check_call([REF_CLI, "-i", str(ours), "-o", str(back1)], stdout=subprocess.DEVNULL)   # reference decodes ours
     subprocess.check_call([cli, "-i", str(ref), "-o", str(back2)])                                     # we decode the reference's
     assert back1.read_bytes() == data.tobytes() and back2.read_bytes() == data.tobytes()
-    assert subprocess.call([cli, "-i", str(src), "-o", str(ours), "-c", "lz78"], stderr=subprocess.DEVNULL) == 255
+    # "-c <anything but lz77>" is lz78 (mc:4040-4043): FCX8 files, interchangeable both ways as well
+    ours8, ref8, back8a, back8b = tmp_path / "ours.fcx8", tmp_path / "ref.fcx8", tmp_path / "back8a.bin", tmp_path / "back8b.bin"
+    subprocess.check_call([cli, "-i", str(src), "-o", str(ours8), "-c", "lz78"])
+    subprocess.check_call([REF_CLI, "-i", str(src), "-o", str(ref8), "-c", "lz78"], stdout=subprocess.DEVNULL)
+    assert ours8.read_bytes() == ref8.read_bytes()
+    subprocess.check_call([REF_CLI, "-i", str(ours8), "-o", str(back8a)], stdout=subprocess.DEVNULL)
+    subprocess.check_call([cli, "-i", str(ref8), "-o", str(back8b)])
+    assert back8a.read_bytes() == back8b.read_bytes()            # the reference's decoder output (it may drop a trailing 0x00)
     # the streaming loop proper: a build whose file pieces are 2 blocks reads / compresses / writes this 3-block
     # file in two overlapped pieces and rewrites the header at the end (mc:4128-4129); same bytes both ways
     small = build.CLI_SMALL
@@ -443,3 +451,34 @@ def test_no_kernel_writes_outside_its_workspace_arrays():
             assert d.guards(True) == 0, family
     finally:
         d.close()
+
+
+def test_lz78_payloads_containers_and_decoder_vs_oracle():
+    """FCX8 (scope row f-3): block payloads and containers byte for byte against the oracle's restatement of
+    my_compress_file_lz78 (pinned against the reference in tests/test_oracle_vs_ref.py), the decoder against the
+    reference decoder's behaviour -- including the unconditional drop of a trailing 0x00 (App. B2) and an input
+    that ends inside a known phrase (mc:1858-1862)."""
+    o = oracle()
+    bufs = [(n, b) for n, b in small_buffers(seed=78, count=24, max_len=5000) if len(b) > 0]
+    bufs.append(("abab", np.frombuffer(b"ABBCBCABABCAABCAAB", np.uint8)))            # SURVEY App. C
+    bufs.append(("ends_in_phrase", np.frombuffer(b"abcabcabcabc" * 9 + b"abc", np.uint8)))
+    bufs.append(("ends_with_zero", np.frombuffer(b"hello world\0", np.uint8)))
+    bufs.append(("zipf300k", datagen.zipf_block(300000, 78, 0)))
+    bufs.append(("uniform1M", datagen.uniform_block(1 << 20, 78, 1)))                # > 256 used ids: group tree + group codes
+    bufs.append(("phrases1M", datagen.phrases_block(1 << 20, 78, 2)))
+    bufs.append(("zeros200k", np.zeros(200000, np.uint8)))                           # phrase k has length k: deep parent chains
+    for name, buf in bufs:
+        want = o.compress_block_lz78(buf)
+        got = api.my_compress_file_lz78(buf)
+        assert got == want, "%s: payload differs at byte %d of %d/%d" % (name, _first_diff(got, want), len(got), len(want))
+        dec_want = o.decompress_block_lz78(want)
+        dec_got = api.my_decompress_file_lz78(want)
+        assert dec_got == dec_want, "%s: decoder differs at byte %d of %d/%d" % (name, _first_diff(dec_got, dec_want), len(dec_got), len(dec_want))
+    data = np.concatenate([datagen.zipf_block(1 << 20, 5, 0), datagen.uniform_block(1 << 20, 5, 1), datagen.phrases_block(70001, 5, 2)])
+    blob = api.compress_lz78(data)
+    assert blob == o.compress_file_lz78(data)
+    assert api.decompress(blob) == o.decompress_file(blob, len(data) + 64)
+    for g in GL["payload_hex"]:                                                       # committed vectors made by the reference build
+        x = np.frombuffer(bytes.fromhex(g["in_hex"]), np.uint8)
+        assert api.my_compress_file_lz78(x).hex() == g["fcx8_block_hex"]
+        assert api.my_decompress_file_lz78(bytes.fromhex(g["fcx8_block_hex"])).hex() == g["ref_decodes_hex"]
