@@ -22,6 +22,7 @@ extern "C" {
 
 #define FCX_BLOCK_BYTES (1u << 20) /* mc:113 BLOCK_BYTES */
 #define FCX_HEADER_BYTES 10u       /* mc:101-109 stCmpFileHead, #pragma pack(1) */
+#define FCX_X9_HEADER_BYTES 16u    /* the opt-in FCX9 container below */
 
 enum {
     FCX_OK = 0,
@@ -85,6 +86,25 @@ int fcx_compress_block_lz78(const uint8_t *in, uint32_t n, uint8_t *out, uint32_
 int fcx_compress_lz78(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_n, uint32_t device_mask);
 int fcx_decompress_block_lz78(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap, uint32_t *out_n);
 
+/* ---- FCX9: opt-in format fixes -- NOT drop-in, the reference cannot read these files --------------
+ * The reference's container has two defects a caller may want to be rid of: the header holds a u32 byte count and a
+ * u16 block count (mc:101-109: an 8 GiB input wraps to 0, more than 65 535 blocks are unrepresentable), and a Huffman
+ * section whose stream holds one distinct symbol drops that symbol (mc:1013-1019), so such blocks decode to zeros
+ * (5000 x 'A', a 1-byte file, 64 distinct bytes).  FCX9 changes exactly those two things:
+ *   header   'F','C','X','9' | u64 total_bytes | u32 n_blocks                  (16 bytes, little-endian)
+ *   records  u32 size | payload, the payload of mc:2115-2253 except that a section with no tree nodes is
+ *            00 | symbol | u32 W = 0  (6 bytes instead of 5) and decodes to `symbol` repeated
+ * Every other byte is what the FCX7 path writes, so a block without a single-symbol stream has the same payload in
+ * both formats; decode(encode(x)) == x for every x.  fcx_compress_bound() covers FCX9 as well.
+ * fcx_decompress_lz77 recognises the magic; the block / record forms need the _x9 twins (a payload has no magic). */
+int fcx_compress_lz77_x9(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_n, uint32_t device_mask);
+int fcx_compress_records_lz77_x9(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_n,
+                                 uint32_t device_mask);
+int fcx_compress_block_lz77_x9(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t out_cap, uint32_t *out_n);
+int fcx_decompress_block_lz77_x9(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap, uint32_t *out_n);
+int fcx_decompress_records_lz77_x9(const uint8_t *records, uint64_t nbytes, uint32_t n_blocks, uint8_t *out,
+                                   uint64_t out_cap, uint64_t *out_n, uint32_t device_mask);
+
 /* Host buffers: any memory works, page-locked memory lets the copies run at full PCIe speed and overlap the
  * kernels (the reference's fread/fwrite buffers, mc:4073 and mc:4088, are what these replace).  NULL on
  * failure.  Pageable buffers are copied through the driver's staging area: correct, but slower. */
@@ -109,6 +129,7 @@ int fcx_ctx_set_stream(fcx_ctx *ctx, void *cuda_stream);
  * larger file passes the whole file's figures on shard 0 and no header elsewhere.
  * Asynchronous on the context's stream; fcx_ctx_finish() synchronises and reports. */
 #define FCX_WITH_HEADER 1u
+#define FCX_FORMAT_X9 2u /* write FCX9 records (and, with FCX_WITH_HEADER, its 16-byte header) instead of FCX7 */
 int fcx_compress_lz77_device(fcx_ctx *ctx, const uint8_t *d_in, uint64_t n, uint8_t *d_out, uint64_t out_cap,
                              uint32_t flags, uint64_t total_bytes_for_header, uint32_t total_blocks_for_header);
 /* Waits for the stream; *out_n = bytes written by the last fcx_compress_lz77_device call. */
@@ -117,9 +138,11 @@ int fcx_ctx_finish(fcx_ctx *ctx, uint64_t *out_n);
 /* Device-resident twin of fcx_decompress_lz77's record loop (mc:4162-4197): the container (or any run of
  * records) lies at d_file, rec_off[b] (host array) is the byte offset of block b's "u32 size | payload" record
  * inside it, block b decodes to d_out + b MiB and its decoded length is returned in lens[b] (host array).
- * d_file must be readable for 16 bytes beyond the last record.  Synchronous. */
+ * d_file must be readable for 16 bytes beyond the last record.  Synchronous.  The _x9 form reads FCX9 records. */
 int fcx_decompress_lz77_device(fcx_ctx *ctx, const uint8_t *d_file, const uint64_t *rec_off, uint32_t n_blocks,
                                uint8_t *d_out, uint32_t *lens);
+int fcx_decompress_lz77_device_x9(fcx_ctx *ctx, const uint8_t *d_file, const uint64_t *rec_off, uint32_t n_blocks,
+                                  uint8_t *d_out, uint32_t *lens);
 
 /* Kernel launches issued on this context since creation (bench.py's gpu_launches). */
 uint64_t fcx_ctx_launch_count(const fcx_ctx *ctx);

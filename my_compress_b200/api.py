@@ -16,6 +16,8 @@ _lib = None
 
 BLOCK_BYTES = 1 << 20
 FCX_WITH_HEADER = 1
+FCX_FORMAT_X9 = 2          # the opt-in FCX9 format (include/fcx.h): 64-bit header fields, named single-symbol sections
+X9_HEADER_BYTES = 16
 
 _u8p = C.POINTER(C.c_uint8)
 
@@ -36,6 +38,8 @@ EXPORTS = [
     "fcx_compress_lz77_device", "fcx_decompress_lz77_device", "fcx_ctx_finish", "fcx_ctx_launch_count", "fcx_ctx_stats", "fcx_ctx_enable_timing",
     "fcx_ctx_stage_times", "fcx_compress_bound_lz78", "fcx_compress_block_lz78", "fcx_compress_lz78", "fcx_decompress_block_lz78",
     "fcx_compress_records_lz77", "fcx_decompress_records_lz77", "fcx_host_alloc", "fcx_host_free",
+    "fcx_compress_lz77_x9", "fcx_compress_records_lz77_x9", "fcx_compress_block_lz77_x9", "fcx_decompress_block_lz77_x9",
+    "fcx_decompress_records_lz77_x9", "fcx_decompress_lz77_device_x9",
     "fcx_ctx_debug_guards", "fcx_probe_match", "fcx_probe_match_auto", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
 ]
 
@@ -61,6 +65,11 @@ def lib():
     L.fcx_compress_block_lz78.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.fcx_compress_lz78.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
     L.fcx_decompress_block_lz78.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.fcx_compress_lz77_x9.argtypes = L.fcx_compress_lz77.argtypes
+    L.fcx_compress_records_lz77_x9.argtypes = L.fcx_compress_records_lz77.argtypes
+    L.fcx_compress_block_lz77_x9.argtypes = L.fcx_compress_block_lz77.argtypes
+    L.fcx_decompress_block_lz77_x9.argtypes = L.fcx_compress_block_lz77.argtypes
+    L.fcx_decompress_records_lz77_x9.argtypes = L.fcx_decompress_records_lz77.argtypes
     L.fcx_host_alloc.restype = C.c_void_p
     L.fcx_host_alloc.argtypes = [C.c_uint64]
     L.fcx_host_free.restype = None
@@ -74,6 +83,7 @@ def lib():
     L.fcx_compress_lz77_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32,
                                            C.c_uint64, C.c_uint32]
     L.fcx_decompress_lz77_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.fcx_decompress_lz77_device_x9.argtypes = L.fcx_decompress_lz77_device.argtypes
     L.fcx_ctx_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.fcx_ctx_launch_count.argtypes = [C.c_void_p]
     L.fcx_ctx_launch_count.restype = C.c_uint64
@@ -169,6 +179,50 @@ def decompress_records(records, n_blocks, n_gpus=1):
     return out[: n.value].tobytes()
 
 
+# ---- FCX9: the opt-in format (64-bit header fields, named single-symbol sections; include/fcx.h) --------------
+
+def compress_x9(data, n_gpus=1):
+    """Whole buffer -> FCX9 container bytes (not readable by the reference; decodes back to exactly ``data``)."""
+    x = _host_u8(data)
+    out = np.empty(compress_bound(len(x)), np.uint8)
+    src = x if len(x) else np.zeros(1, np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_compress_lz77_x9(src.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+def compress_records_x9(data, n_gpus=1):
+    x = _host_u8(data)
+    out = np.empty(compress_bound(len(x)), np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_compress_records_lz77_x9(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+def decompress_records_x9(records, n_blocks, n_gpus=1):
+    x = _host_u8(records)
+    out = np.empty(max(1, n_blocks) * (BLOCK_BYTES + 8), np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().fcx_decompress_records_lz77_x9(x.ctypes.data, len(x), int(n_blocks), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
+    return out[: n.value].tobytes()
+
+
+def compress_block_x9(data):
+    x = _host_u8(data)
+    out = np.empty(compress_bound(len(x)), np.uint8)
+    n = C.c_uint32(0)
+    _check(lib().fcx_compress_block_lz77_x9(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def decompress_block_x9(payload):
+    x = _host_u8(payload)
+    out = np.empty(BLOCK_BYTES + 8, np.uint8)
+    n = C.c_uint32(0)
+    _check(lib().fcx_decompress_block_lz77_x9(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n)))
+    return out[: n.value].tobytes()
+
+
 # ---- lz78 / FCX8 twins (mc:3127, mc:3478; "-c <anything but lz77>" of the reference CLI) -------------------
 
 def my_compress_file_lz78(data):
@@ -234,6 +288,10 @@ def decompress(blob, n_gpus=1):
     if len(x) < 10:
         raise FcxError(-5, "shorter than the 10-byte header")
     nb = int.from_bytes(x[8:10].tobytes(), "little")
+    if x[3] == ord("9"):                                       # FCX9: u64 byte count, u32 block count
+        if len(x) < X9_HEADER_BYTES:
+            raise FcxError(-5, "shorter than the 16-byte FCX9 header")
+        nb = min(int.from_bytes(x[12:16].tobytes(), "little"), len(x) // 4)
     out = np.empty(max(1, nb) * (BLOCK_BYTES + 8), np.uint8)
     n = C.c_uint64(0)
     _check(lib().fcx_decompress_lz77(x.ctypes.data, len(x), out.ctypes.data, len(out), C.byref(n), device_mask(n_gpus)))
@@ -285,12 +343,12 @@ class DeviceCompressor:
         except Exception:
             pass
 
-    def compress_async(self, d_in, d_out, with_header=True, header_bytes=None, header_blocks=None, n=None):
+    def compress_async(self, d_in, d_out, with_header=True, header_bytes=None, header_blocks=None, n=None, x9=False):
         n = int(d_in.numel() if n is None else n)
         hb = n if header_bytes is None else int(header_bytes)
         hk = (n + BLOCK_BYTES - 1) // BLOCK_BYTES if header_blocks is None else int(header_blocks)
         _check(lib().fcx_compress_lz77_device(self._ctx, C.c_void_p(d_in.data_ptr()), n, C.c_void_p(d_out.data_ptr()),
-                                              int(d_out.numel()), FCX_WITH_HEADER if with_header else 0, hb, hk & 0xFFFFFFFF))
+                                              int(d_out.numel()), (FCX_WITH_HEADER if with_header else 0) | (FCX_FORMAT_X9 if x9 else 0), hb, hk & 0xFFFFFFFF))
 
     def finish(self):
         n = C.c_uint64(0)
@@ -303,11 +361,12 @@ class DeviceCompressor:
         self.compress_async(d_in, d_out, **kw)
         return d_out, self.finish()
 
-    def decompress(self, d_file, rec_off, d_out):
+    def decompress(self, d_file, rec_off, d_out, x9=False):
         """Device-resident decode: block b of the records at ``rec_off`` (numpy uint64) -> d_out[b MiB:]; returns lens."""
         rec = np.ascontiguousarray(rec_off, dtype=np.uint64)
         lens = np.zeros(len(rec), np.uint32)
-        _check(lib().fcx_decompress_lz77_device(self._ctx, C.c_void_p(d_file.data_ptr()), rec.ctypes.data, len(rec),
+        fn = lib().fcx_decompress_lz77_device_x9 if x9 else lib().fcx_decompress_lz77_device
+        _check(fn(self._ctx, C.c_void_p(d_file.data_ptr()), rec.ctypes.data, len(rec),
                                                 C.c_void_p(d_out.data_ptr()), lens.ctypes.data))
         return lens
 

@@ -1,5 +1,5 @@
 // fcx_cli -- flag-compatible stand-in for the reference CLI (SURVEY 8f "next" row 2):
-//     ./fcx_cli -i <in> [-o <out>] [-c lz77] [-g <gpus>]     (mc:3992-4053: no -c => decompress, default out "./out")
+//     ./fcx_cli -i <in> [-o <out>] [-c lz77|fcx9] [-g <gpus>]     (mc:3992-4053: no -c => decompress, default out "./out")
 //
 // Same file loop as the reference's main(), with the three steps of every iteration running side by side:
 //   compress   (mc:4073-4136)  placeholder header, then per piece  fread -> fcx_compress_records_lz77 -> fwrite,
@@ -107,7 +107,7 @@ bool run_pipeline(Pipe &p, Fill fill, Work work, Drain drain)
 int main(int argc, char **argv)
 {
     if (argc != 3 && argc != 4 && argc != 5 && argc != 7 && argc != 9) {           // mc:3992 (+ "-g n")
-        fprintf(stderr, "usage: %s -i <input> [-o <output>] [-c lz77] [-g <gpus>]\n", argv[0]);
+        fprintf(stderr, "usage: %s -i <input> [-o <output>] [-c lz77|lz78|fcx9] [-g <gpus>]\n", argv[0]);
         return 255;
     }
     static struct option longOpts[] = {{"file_in", required_argument, nullptr, 'i'},
@@ -124,7 +124,10 @@ int main(int argc, char **argv)
         else if (opt == 'c' && optarg) { algo = optarg; compress = true; }
         else if (opt == 'g' && optarg) gpus = atoi(optarg);
     }
-    const bool lz78 = compress && strncmp(algo.c_str(), "lz77", 4) != 0;     // mc:4040-4043: anything else means lz78
+    // "-c fcx9": the opt-in format of include/fcx.h (64-bit header fields, named single-symbol sections) -- the one
+    // spelling that does not mean what it means to the reference (there, anything but lz77 is lz78)
+    const bool x9 = compress && algo == "fcx9";
+    const bool lz78 = compress && !x9 && strncmp(algo.c_str(), "lz77", 4) != 0;     // mc:4040-4043: anything else means lz78
     const int nd = fcx_device_count();
     if (nd == 0) { fprintf(stderr, "fcx: no CUDA device (this path has no CPU fallback)\n"); return 255; }
     gpus = gpus < 1 ? 1 : gpus > nd ? nd : gpus;
@@ -175,8 +178,9 @@ int main(int argc, char **argv)
     uint64_t totalIn = 0, totalBlocks = 0;
     auto drain = [&](Slot &s) { return s.outBytes == 0 || fwrite(s.out, 1, s.outBytes, fout) == s.outBytes; };
     if (compress) {
-        uint8_t head[FCX_HEADER_BYTES] = {'F', 'C', 'X', '7', 0, 0, 0, 0, 0, 0};
-        ok = fwrite(head, 1, sizeof head, fout) == sizeof head;                  // placeholder, mc:4078-4086
+        uint8_t head[FCX_X9_HEADER_BYTES] = {'F', 'C', 'X', (uint8_t)(x9 ? '9' : '7'), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t headLen = x9 ? FCX_X9_HEADER_BYTES : FCX_HEADER_BYTES;
+        ok = fwrite(head, 1, headLen, fout) == headLen;                          // placeholder, mc:4078-4086
         if (ok) ok = run_pipeline(p,
             [&](Slot &s) {                                                       // mc:4090: fread up to one piece
                 s.inBytes = fread(s.in, 1, kPieceBytes, fin);
@@ -186,22 +190,28 @@ int main(int argc, char **argv)
             },
             [&](Slot &s) {
                 s.outBytes = 0;
-                return s.inBytes == 0 || fcx_compress_records_lz77(s.in, s.inBytes, s.out, outCap, &s.outBytes, mask) == FCX_OK;
+                if (s.inBytes == 0) return true;
+                return (x9 ? fcx_compress_records_lz77_x9(s.in, s.inBytes, s.out, outCap, &s.outBytes, mask)
+                           : fcx_compress_records_lz77(s.in, s.inBytes, s.out, outCap, &s.outBytes, mask)) == FCX_OK;
             },
             drain);
         if (ok) {                                                                // mc:4128-4129: the real header
             const uint32_t tb = (uint32_t)totalIn;                               // uInt32 cmp_before_bytes wraps (mc:105)
             const uint16_t bn = (uint16_t)totalBlocks;                           // uInt16 block_num wraps (mc:106)
-            memcpy(head + 4, &tb, 4); memcpy(head + 8, &bn, 2);
-            ok = fseek(fout, 0, SEEK_SET) == 0 && fwrite(head, 1, sizeof head, fout) == sizeof head;
+            if (x9) { const uint32_t bn32 = (uint32_t)totalBlocks; memcpy(head + 4, &totalIn, 8); memcpy(head + 12, &bn32, 4); }
+            else { memcpy(head + 4, &tb, 4); memcpy(head + 8, &bn, 2); }
+            ok = fseek(fout, 0, SEEK_SET) == 0 && fwrite(head, 1, headLen, fout) == headLen;
         }
     } else {
-        uint8_t head[FCX_HEADER_BYTES];
-        if (fread(head, 1, sizeof head, fin) != sizeof head) { fprintf(stderr, "Read file head infomation error!!!\n"); return 255; }   // mc:4139-4144
-        if (memcmp(head, "FCX", 3) != 0 || head[3] != '7') { fprintf(stderr, "not an FCX7 file\n"); return 255; }                     // mc:4146-4152
-        uint16_t blocks;
-        memcpy(&blocks, head + 8, 2);
-        uint32_t left = blocks;
+        uint8_t head[FCX_X9_HEADER_BYTES];
+        if (fread(head, 1, FCX_HEADER_BYTES, fin) != FCX_HEADER_BYTES) { fprintf(stderr, "Read file head infomation error!!!\n"); return 255; }   // mc:4139-4144
+        if (memcmp(head, "FCX", 3) != 0 || (head[3] != '7' && head[3] != '9')) { fprintf(stderr, "not an FCX7 / FCX9 file\n"); return 255; }     // mc:4146-4152
+        const bool in9 = head[3] == '9';
+        uint32_t left;
+        if (in9) {
+            if (fread(head + FCX_HEADER_BYTES, 1, 6, fin) != 6) { fprintf(stderr, "Read file head infomation error!!!\n"); return 255; }
+            memcpy(&left, head + 12, 4);
+        } else { uint16_t blocks; memcpy(&blocks, head + 8, 2); left = blocks; }
         ok = run_pipeline(p,
             [&](Slot &s) {                                                       // mc:4162-4174: whole records, up to one piece
                 s.inBytes = 0; s.blocks = 0;
@@ -222,7 +232,9 @@ int main(int argc, char **argv)
             },
             [&](Slot &s) {
                 s.outBytes = 0;
-                return s.blocks == 0 || fcx_decompress_records_lz77(s.in, s.inBytes, s.blocks, s.out, outCap, &s.outBytes, mask) == FCX_OK;
+                if (s.blocks == 0) return true;
+                return (in9 ? fcx_decompress_records_lz77_x9(s.in, s.inBytes, s.blocks, s.out, outCap, &s.outBytes, mask)
+                            : fcx_decompress_records_lz77(s.in, s.inBytes, s.blocks, s.out, outCap, &s.outBytes, mask)) == FCX_OK;
             },
             drain);
     }

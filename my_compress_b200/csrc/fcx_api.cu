@@ -246,12 +246,13 @@ int fcx::run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out
     if (nBlocks == 0) {
         if (flags & FCX_WITH_HEADER) {
             // empty input: header only, block_num = 0
-            uint8_t h[10] = {'F', 'C', 'X', '7', 0, 0, 0, 0, 0, 0};
+            uint8_t h[16] = {'F', 'C', 'X', '7', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             uint32_t tb = (uint32_t)hdrBytes; uint16_t bn = (uint16_t)hdrBlocks;
-            memcpy(h + 4, &tb, 4); memcpy(h + 8, &bn, 2);
-            if (outCap < 10) return fail(FCX_ERR_CAPACITY, "output buffer too small");
-            const uint64_t ten = 10;
-            CK(cudaMemcpyAsync(d_out, h, 10, cudaMemcpyHostToDevice, st));
+            uint64_t ten = FCX_HEADER_BYTES;
+            if (flags & FCX_FORMAT_X9) { h[3] = '9'; memcpy(h + 4, &hdrBytes, 8); memcpy(h + 12, &hdrBlocks, 4); ten = FCX_X9_HEADER_BYTES; }
+            else { memcpy(h + 4, &tb, 4); memcpy(h + 8, &bn, 2); }
+            if (outCap < ten) return fail(FCX_ERR_CAPACITY, "output buffer too small");
+            CK(cudaMemcpyAsync(d_out, h, ten, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(w.counters + C_CURSOR, &ten, 8, cudaMemcpyHostToDevice, st));
             CK(cudaStreamSynchronize(st));                              // h / ten are stack variables
         }
@@ -267,7 +268,7 @@ int fcx::run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out
         const uint8_t *bin = d_in + first * kBlockBytes;
         const uint64_t rem = n - first * kBlockBytes;
         const uint32_t maxLen = (uint32_t)std::min<uint64_t>(rem, kBlockBytes);
-        const uint32_t withHeader = (first == 0 && (flags & FCX_WITH_HEADER)) ? 1u : 0u;
+        const uint32_t batchFlags = (flags & FCX_FORMAT_X9) | ((first == 0 && (flags & FCX_WITH_HEADER)) ? FCX_WITH_HEADER : 0u);
         mark_stage(c, -1);
         // edge words of every chunk are merged with atomicOr, so the part of the destination this batch can
         // reach starts out zero (the running cursor lives on the device: the kernel reads it there)
@@ -277,7 +278,7 @@ int fcx::run_batches(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d_out
         mark_stage(c, ST_MATCH);
         c->launches += 3 + launch_parse(bin, w.blkLen, w, nb, maxLen, st);
         mark_stage(c, ST_PARSE);
-        c->launches += launch_huff_stage(w, nb, d_out, outCap, withHeader, (uint32_t)hdrBytes, hdrBlocks, 0, c->numSM, st,
+        c->launches += launch_huff_stage(w, nb, d_out, outCap, batchFlags, hdrBytes, hdrBlocks, 0, c->numSM, st,
                                          mark_stage, c);
         CK(cudaGetLastError());
         if (hooks && hooks->recordAfter) {
@@ -333,8 +334,23 @@ extern "C" int fcx_ctx_stats(fcx_ctx *c, fcx_stats *s)
 // -----------------------------------------------------------------------------------------
 // device-resident decompress
 // -----------------------------------------------------------------------------------------
+static int decompress_device(fcx_ctx *c, const uint8_t *d_file, const uint64_t *recOff, uint32_t nBlocks, uint8_t *d_out,
+                             uint32_t *lens, bool x9);
+
 extern "C" int fcx_decompress_lz77_device(fcx_ctx *c, const uint8_t *d_file, const uint64_t *recOff, uint32_t nBlocks,
                                           uint8_t *d_out, uint32_t *lens)
+{
+    return decompress_device(c, d_file, recOff, nBlocks, d_out, lens, false);
+}
+
+extern "C" int fcx_decompress_lz77_device_x9(fcx_ctx *c, const uint8_t *d_file, const uint64_t *recOff, uint32_t nBlocks,
+                                             uint8_t *d_out, uint32_t *lens)
+{
+    return decompress_device(c, d_file, recOff, nBlocks, d_out, lens, true);
+}
+
+static int decompress_device(fcx_ctx *c, const uint8_t *d_file, const uint64_t *recOff, uint32_t nBlocks, uint8_t *d_out,
+                             uint32_t *lens, bool x9)
 {
     if (!c || !d_file || !recOff || !d_out || !lens) return fail(FCX_ERR_ARG, "null pointer");
     if (nBlocks == 0) return FCX_OK;
@@ -351,7 +367,7 @@ extern "C" int fcx_decompress_lz77_device(fcx_ctx *c, const uint8_t *d_file, con
         const uint32_t nb = std::min(kBatch, nBlocks - b0);
         // pageable source: the copy returns once the offsets are staged, so the caller's array may change afterwards
         CK(cudaMemcpyAsync(c->decRec, recOff + b0, sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, st));
-        c->launches += launch_decode(d_file, c->decRec, nb, d_out + (size_t)b0 * kBlockBytes, c->decLen, c->decScratch, per, st);
+        c->launches += launch_decode(d_file, c->decRec, nb, d_out + (size_t)b0 * kBlockBytes, c->decLen, c->decScratch, per, st, x9);
         CK(cudaMemcpyAsync(lens + b0, c->decLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));

@@ -47,6 +47,7 @@ size_t decode_scratch_per_block() { return DEC_SCRATCH; }
 struct DecMeta {
     uint32_t T, Pc, G, bad;
     uint32_t secOff[4], secCnt[4], secTn[4], secW[4], secRaw[4];
+    uint32_t secSym[4];                // FCX9: 0x100 | symbol of a single-symbol section (0 otherwise)
     uint32_t nL;                       // l values the Golomb stream really held (k_dec_replay)
 };
 static_assert(sizeof(DecMeta) <= 256, "the record fits its scratch slot");
@@ -55,13 +56,16 @@ static_assert(sizeof(DecMeta) <= 256, "the record fits its scratch slot");
 // 1: section headers
 // =========================================================================================
 // Parses one section header at payload offset `at`; returns the offset just past the section.
-__device__ uint32_t parse_section(DecMeta &m, int k, const uint8_t *pl, uint32_t plen, uint32_t at, uint32_t cnt)
+// x9: the opt-in FCX9 format, where a section without tree nodes carries its one symbol behind the zero count.
+__device__ uint32_t parse_section(DecMeta &m, int k, const uint8_t *pl, uint32_t plen, uint32_t at, uint32_t cnt, bool x9)
 {
-    m.secCnt[k] = cnt; m.secRaw[k] = 0; m.secOff[k] = at; m.secTn[k] = 0; m.secW[k] = 0;
+    m.secCnt[k] = cnt; m.secRaw[k] = 0; m.secOff[k] = at; m.secTn[k] = 0; m.secW[k] = 0; m.secSym[k] = 0;
     if (at + 5 > plen) { m.bad = 1; return at; }
     const uint32_t Tn = pl[at];
     const uint32_t mapB = (2 * Tn + 7) / 8;
-    const uint32_t wAt = at + 1 + mapB + 2 * Tn;
+    const uint32_t named = (x9 && Tn == 0) ? 1u : 0u;
+    if (named) m.secSym[k] = 0x100u | pl[at + 1];                   // at + 5 <= plen: the byte is there
+    const uint32_t wAt = at + 1 + named + mapB + 2 * Tn;
     if (wAt + 4 > plen) { m.bad = 1; return at; }
     const uint32_t W = rd32(pl + wAt);
     if ((unsigned long long)wAt + 4 + 4ull * W > plen) { m.bad = 1; return at; }
@@ -71,7 +75,7 @@ __device__ uint32_t parse_section(DecMeta &m, int k, const uint8_t *pl, uint32_t
 
 __global__ void __launch_bounds__(128)
 k_dec_parse(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOff, uint32_t nBlocks,
-            uint8_t *__restrict__ scratchAll, size_t scratchPerBlock)
+            uint8_t *__restrict__ scratchAll, size_t scratchPerBlock, bool x9)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nBlocks) return;
@@ -80,7 +84,7 @@ k_dec_parse(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOf
     const uint8_t *pl = rec + 4;
     DecMeta m;
     m.T = m.Pc = m.G = m.bad = m.nL = 0;
-    for (int k = 0; k < 4; k++) { m.secOff[k] = m.secCnt[k] = m.secTn[k] = m.secW[k] = m.secRaw[k] = 0; }
+    for (int k = 0; k < 4; k++) { m.secOff[k] = m.secCnt[k] = m.secTn[k] = m.secW[k] = m.secRaw[k] = m.secSym[k] = 0; }
     if (plen < 4) m.bad = 1;
     else {
         const uint32_t T = rd32(pl);
@@ -89,21 +93,21 @@ k_dec_parse(const uint8_t *__restrict__ file, const uint64_t *__restrict__ recOf
         else {
             uint32_t at = 4;
             const uint32_t mapB = (T + 7) / 8;
-            if (mapB > 1) at = parse_section(m, 0, pl, plen, at, mapB);            // mc:2273-2276
+            if (mapB > 1) at = parse_section(m, 0, pl, plen, at, mapB, x9);            // mc:2273-2276
             else { m.secRaw[0] = 1; m.secOff[0] = at; m.secCnt[0] = mapB;
                    if (at + mapB > plen) m.bad = 1; at += mapB; }                    // mc:2277-2280
-            if (!m.bad) at = parse_section(m, 1, pl, plen, at, T);                 // mc:2283
+            if (!m.bad) at = parse_section(m, 1, pl, plen, at, T, x9);                 // mc:2283
             if (!m.bad && at + 4 <= plen) {
                 m.Pc = rd32(pl + at); at += 4;                                     // mc:2286
                 if (m.Pc > DEC_MAX_PC) m.bad = 1;
             } else m.bad = 1;
-            if (!m.bad) at = parse_section(m, 2, pl, plen, at, (kPBits * m.Pc) / 8 + 1);   // mc:2290-2292
+            if (!m.bad) at = parse_section(m, 2, pl, plen, at, (kPBits * m.Pc) / 8 + 1, x9);   // mc:2290-2292
             if (!m.bad && at + 4 <= plen) {
                 m.G = rd32(pl + at); at += 4;                                      // mc:2302
                 if (m.G > 105216 / 4) m.bad = 1;
             } else m.bad = 1;
             if (!m.bad) {
-                if (m.G) at = parse_section(m, 3, pl, plen, at, m.G * 4);          // mc:2308
+                if (m.G) at = parse_section(m, 3, pl, plen, at, m.G * 4, x9);          // mc:2308
                 else { m.secCnt[3] = 0; m.secW[3] = 0; m.secTn[3] = 0; m.secRaw[3] = 0; m.secOff[3] = at; }   // App. B8
             }
         }
@@ -138,7 +142,13 @@ k_dec_sections(const uint8_t *__restrict__ file, const uint64_t *__restrict__ re
         for (uint32_t i = tid; i < cnt; i += DEC_THREADS) d[i] = pl[at + i];
         return;
     }
-    // Tn == 0 (single-symbol stream): nothing is decoded, the zero-filled buffer stands (App. B1)
+    // Tn == 0 (single-symbol stream): nothing is decoded, the zero-filled buffer stands (App. B1) -- unless the
+    // section names its symbol (FCX9)
+    if (meta->secSym[k]) {
+        const uint8_t sym = (uint8_t)meta->secSym[k];
+        for (uint32_t i = tid; i < cnt; i += DEC_THREADS) d[i] = sym;
+        return;
+    }
     if (!(cnt && Tn && W)) return;
     const uint32_t mapB = (2 * Tn + 7) / 8;
     for (uint32_t i = tid; i < mapB; i += DEC_THREADS) sm.map[i] = pl[at + 1 + i];
@@ -379,11 +389,11 @@ void decode_init()
 }
 
 int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out,
-                  uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st)
+                  uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st, bool x9)
 {
     // the reference decodes into zero-initialised buffers (mc:2270,2282,2291,2305)
     cudaMemsetAsync(d_scratch, 0, scratchPerBlock * nBlocks, st);
-    k_dec_parse<<<(nBlocks + 127) / 128, 128, 0, st>>>(d_file, d_recOff, nBlocks, d_scratch, scratchPerBlock);
+    k_dec_parse<<<(nBlocks + 127) / 128, 128, 0, st>>>(d_file, d_recOff, nBlocks, d_scratch, scratchPerBlock, x9);
     k_dec_sections<<<dim3(4, nBlocks), DEC_THREADS, 0, st>>>(d_file, d_recOff, d_scratch, scratchPerBlock);
     k_dec_replay<<<nBlocks, DEC_THREADS, sizeof(ReplaySmem), st>>>(d_out, d_outLen, d_scratch, scratchPerBlock);
     return 3;

@@ -172,8 +172,9 @@ std::vector<int> devices_of(uint32_t mask, int nd)
 }
 
 // compress `n` bytes into records (+ the file header when withHeader) over the devices of `mask`
+// fmt: 0 = FCX7 (the reference's bytes), FCX_FORMAT_X9 = the opt-in format (include/fcx.h)
 int compress_host(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, uint64_t *outN, uint32_t mask,
-                  bool withHeader, uint64_t hdrBytes, uint64_t hdrBlocks)
+                  bool withHeader, uint64_t hdrBytes, uint64_t hdrBlocks, uint32_t fmt = 0)
 {
     if (!out || !outN || (!in && n)) return fail(FCX_ERR_ARG, "null pointer");      // mc:2122-2123 returns 0 here
     const int nd = fcx_device_count();
@@ -181,7 +182,7 @@ int compress_host(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, 
     const std::vector<int> devs = devices_of(mask, nd);
     if (devs.empty()) return fail(FCX_ERR_ARG, "device_mask selects no visible device");
     const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
-    if (withHeader && outCap < FCX_HEADER_BYTES) return fail(FCX_ERR_CAPACITY, "output buffer too small");
+    if (withHeader && outCap < (fmt ? FCX_X9_HEADER_BYTES : FCX_HEADER_BYTES)) return fail(FCX_ERR_CAPACITY, "output buffer too small");
     const size_t G = (size_t)std::min<uint64_t>(devs.size(), std::max<uint64_t>(1, nBlocks));
 
     // ---- deal the batches: round k gives every device plan[k] consecutive blocks -----------------------------
@@ -205,7 +206,7 @@ int compress_host(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, 
         std::lock_guard<std::mutex> lk(s.mu);
         int rc = slot_prepare_compress(s, devs[0], 16, 64, 1);
         if (rc) return rc;
-        rc = fcx_compress_lz77_device(s.ctx, s.dIn, 0, s.dOut, 64, withHeader ? FCX_WITH_HEADER : 0, hdrBytes, (uint32_t)hdrBlocks);
+        rc = fcx_compress_lz77_device(s.ctx, s.dIn, 0, s.dOut, 64, (withHeader ? FCX_WITH_HEADER : 0) | fmt, hdrBytes, (uint32_t)hdrBlocks);
         uint64_t got = 0;
         if (rc == FCX_OK) rc = fcx_ctx_finish(s.ctx, &got);
         if (rc) return rc;
@@ -256,7 +257,7 @@ int compress_host(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, 
             hooks.sizes = sizes.data(); hooks.nSizes = (uint32_t)sizes.size();
             s.ctx->batchBlocks = 0;
             const bool first = withHeader && my[0] == 0;
-            rc = run_batches(s.ctx, s.dIn, localBytes, s.dOut, bound, first ? FCX_WITH_HEADER : 0, hdrBytes, (uint32_t)hdrBlocks, &hooks);
+            rc = run_batches(s.ctx, s.dIn, localBytes, s.dOut, bound, (first ? FCX_WITH_HEADER : 0) | fmt, hdrBytes, (uint32_t)hdrBlocks, &hooks);
         }
         // ---- downloads: each batch goes to its final place as soon as the batches before it have reported -----------
         uint64_t prev = 0;
@@ -309,7 +310,7 @@ extern "C" int fcx_compress_records_lz77(const uint8_t *in, uint64_t n, uint8_t 
     return compress_host(in, n, out, outCap, outN, deviceMask, false, 0, 0);
 }
 
-extern "C" int fcx_compress_block_lz77(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t outCap, uint32_t *outN)
+static int compress_block_host(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t outCap, uint32_t *outN, uint32_t fmt)
 {
     if (!in || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");             // mc:2122-2123
     if (n == 0 || n > kBlockBytes) return fail(FCX_ERR_ARG, "a block holds 1..1048576 bytes (mc:4090)");
@@ -321,7 +322,7 @@ extern "C" int fcx_compress_block_lz77(const uint8_t *in, uint32_t n, uint8_t *o
     if (rc) return rc;
     CK(cudaMemcpyAsync(s.dIn, in, n, cudaMemcpyHostToDevice, s.stream));
     s.ctx->batchBlocks = 0;
-    rc = fcx_compress_lz77_device(s.ctx, s.dIn, n, s.dOut, bound, 0, 0, 0);
+    rc = fcx_compress_lz77_device(s.ctx, s.dIn, n, s.dOut, bound, fmt, 0, 0);
     uint64_t bytes = 0;
     const int frc = fcx_ctx_finish(s.ctx, &bytes);                                  // always: nothing stays in flight
     if (rc == FCX_OK) rc = frc;
@@ -333,6 +334,32 @@ extern "C" int fcx_compress_block_lz77(const uint8_t *in, uint32_t n, uint8_t *o
     return FCX_OK;
 }
 
+extern "C" int fcx_compress_block_lz77(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t outCap, uint32_t *outN)
+{
+    return compress_block_host(in, n, out, outCap, outN, 0);
+}
+
+// ---- FCX9: the opt-in format (64-bit header fields, named single-symbol sections); not readable by the reference ----
+extern "C" int fcx_compress_lz77_x9(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, uint64_t *outN,
+                                    uint32_t deviceMask)
+{
+    const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
+    if (nBlocks > 0xFFFFFFFFull) return fail(FCX_ERR_UNSUPPORTED, "more than 2^32 - 1 blocks");
+    return compress_host(in, n, out, outCap, outN, deviceMask, true, n, nBlocks, FCX_FORMAT_X9);
+}
+
+extern "C" int fcx_compress_records_lz77_x9(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, uint64_t *outN,
+                                            uint32_t deviceMask)
+{
+    if (n == 0) { if (outN) *outN = 0; return (out && outN) ? FCX_OK : fail(FCX_ERR_ARG, "null pointer"); }
+    return compress_host(in, n, out, outCap, outN, deviceMask, false, 0, 0, FCX_FORMAT_X9);
+}
+
+extern "C" int fcx_compress_block_lz77_x9(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t outCap, uint32_t *outN)
+{
+    return compress_block_host(in, n, out, outCap, outN, FCX_FORMAT_X9);
+}
+
 // -----------------------------------------------------------------------------------------
 // decompress (device kernels in fcx_decode.cu)
 // -----------------------------------------------------------------------------------------
@@ -340,7 +367,7 @@ namespace {
 
 // records: offsets of the "u32 size | payload" records inside `file`; recEnd = end of the last one
 int decompress_host(const uint8_t *file, const std::vector<uint64_t> &rec, uint64_t recEnd, uint8_t *out, uint64_t outCap,
-                    uint64_t *outN, uint32_t mask)
+                    uint64_t *outN, uint32_t mask, bool x9 = false)
 {
     const int nd = fcx_device_count();
     if (nd == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
@@ -470,7 +497,7 @@ int decompress_host(const uint8_t *file, const std::vector<uint64_t> &rec, uint6
             const GBatch &b = batches[my[k]];
             cuda_ok(cudaStreamWaitEvent(s.stream, s.evIn[k], 0), "wait");
             launch_decode(s.dIn, s.decRec + blk0[k], b.nBlocks, s.dOut + (uint64_t)(k % kDecRing) * maxBatch * kBlockBytes,
-                          s.decLen + blk0[k], s.decScratch, per, s.stream);
+                          s.decLen + blk0[k], s.decScratch, per, s.stream, x9);
             cuda_ok(cudaMemcpyAsync(s.hostLen + blk0[k], s.decLen + blk0[k], sizeof(uint32_t) * b.nBlocks, cudaMemcpyDeviceToHost, s.stream), "D2H");
             cuda_ok(cudaEventRecord(s.evOut[k], s.stream), "event");
         }
@@ -521,10 +548,23 @@ extern "C" int fcx_decompress_lz77(const uint8_t *file, uint64_t nbytes, uint8_t
     if (!file || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");
     if (nbytes < 10) return fail(FCX_ERR_FORMAT, "shorter than the 10-byte header");               // mc:4139-4144
     if (memcmp(file, "FCX", 3) != 0) return fail(FCX_ERR_FORMAT, "not an FCX container");          // mc:4146-4152
-    if (file[3] != '7' && file[3] != '8') return fail(FCX_ERR_FORMAT, "not an FCX7 / FCX8 container");   // mc:4153-4164
+    if (file[3] != '7' && file[3] != '8' && file[3] != '9') return fail(FCX_ERR_FORMAT, "not an FCX7 / FCX8 / FCX9 container");   // mc:4153-4164
     if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
-    uint16_t nb16; memcpy(&nb16, file + 8, 2);
     std::vector<uint64_t> rec;
+    if (file[3] == '9') {                                  // opt-in format: u64 byte count, u32 block count
+        if (nbytes < FCX_X9_HEADER_BYTES) return fail(FCX_ERR_FORMAT, "shorter than the 16-byte FCX9 header");
+        uint64_t total; uint32_t nb32;
+        memcpy(&total, file + 4, 8); memcpy(&nb32, file + 12, 4);
+        if ((total + kBlockBytes - 1) / kBlockBytes != nb32) return fail(FCX_ERR_FORMAT, "FCX9 header: block count does not match the byte count");
+        if ((uint64_t)nb32 * 4 > nbytes) return fail(FCX_ERR_FORMAT, "truncated FCX9 container");
+        uint64_t end9 = FCX_X9_HEADER_BYTES;
+        int rc9 = scan_records(file, nbytes, FCX_X9_HEADER_BYTES, nb32, rec, end9);
+        if (rc9) return rc9;
+        rc9 = decompress_host(file, rec, end9, out, outCap, outN, deviceMask, true);
+        if (rc9 == FCX_OK && *outN != total) return fail(FCX_ERR_FORMAT, "FCX9: decoded byte count differs from the header");
+        return rc9;
+    }
+    uint16_t nb16; memcpy(&nb16, file + 8, 2);
     uint64_t end = 10;
     int rc = scan_records(file, nbytes, 10, nb16, rec, end);
     if (rc) return rc;
@@ -544,8 +584,33 @@ extern "C" int fcx_decompress_records_lz77(const uint8_t *records, uint64_t nbyt
     return decompress_host(records, rec, end, out, outCap, outN, deviceMask);
 }
 
+static int decompress_block_host(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t outCap, uint32_t *outN, bool x9);
+
 extern "C" int fcx_decompress_block_lz77(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t outCap,
                                          uint32_t *outN)
+{
+    return decompress_block_host(payload, nbytes, out, outCap, outN, false);
+}
+
+extern "C" int fcx_decompress_block_lz77_x9(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t outCap,
+                                            uint32_t *outN)
+{
+    return decompress_block_host(payload, nbytes, out, outCap, outN, true);
+}
+
+extern "C" int fcx_decompress_records_lz77_x9(const uint8_t *records, uint64_t nbytes, uint32_t nBlocks, uint8_t *out,
+                                              uint64_t outCap, uint64_t *outN, uint32_t deviceMask)
+{
+    if (!records || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");
+    if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+    std::vector<uint64_t> rec;
+    uint64_t end = 0;
+    int rc = scan_records(records, nbytes, 0, nBlocks, rec, end);
+    if (rc) return rc;
+    return decompress_host(records, rec, end, out, outCap, outN, deviceMask, true);
+}
+
+static int decompress_block_host(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t outCap, uint32_t *outN, bool x9)
 {
     if (!payload || !out || !outN) return fail(FCX_ERR_ARG, "null pointer");                      // mc:2257-2258
     if (fcx_device_count() == 0) return fail(FCX_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
@@ -554,7 +619,7 @@ extern "C" int fcx_decompress_block_lz77(const uint8_t *payload, uint32_t nbytes
     memcpy(rec.data() + 4, payload, nbytes);
     std::vector<uint64_t> off(1, 0);
     uint64_t got = 0;
-    int rc = decompress_host(rec.data(), off, rec.size(), out, outCap, &got, 1);
+    int rc = decompress_host(rec.data(), off, rec.size(), out, outCap, &got, 1, x9);
     if (rc) return rc;
     *outN = (uint32_t)got;
     return FCX_OK;

@@ -18,6 +18,7 @@
 // into the container (the sections sit at odd byte offsets, so everything is addressed as one
 // little-endian bit stream over the 4-byte aligned output buffer).
 #include "fcx_dev.cuh"
+#include "../../include/fcx.h"   // FCX_WITH_HEADER, FCX_FORMAT_X9, header sizes
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -141,7 +142,7 @@ struct TreeSmem {
 };
 
 __global__ void __launch_bounds__(256)
-k_tree(Ws ws, uint32_t nSeg)
+k_tree(Ws ws, uint32_t nSeg, uint32_t escape)
 {
     __shared__ TreeSmem sm;
     const int t = threadIdx.x;
@@ -240,8 +241,12 @@ k_tree(Ws ws, uint32_t nSeg)
         const uint32_t ci = sm.child[j];
         sm.hdr[1 + mapB + j] = (uint8_t)(ci >= 256 ? ci - 256 : ci);
     }
+    // FCX9 (opt-in format, include/fcx.h): a single-symbol stream names its symbol after the zero node count, so it
+    // decodes to what was encoded (the FCX7 section drops it, mc:1013-1019)
+    const bool named = escape && R == 1;
+    if (t == 0 && named) sm.hdr[1] = sm.ssym[0];
     __syncthreads();
-    const uint32_t hdrBytes = 1 + mapB + 2 * Tn;
+    const uint32_t hdrBytes = 1 + mapB + 2 * Tn + (named ? 1u : 0u);
     for (uint32_t i = t; i < hdrBytes; i += 256) ws.segHdr[(size_t)s * kSegHdrStride + i] = sm.hdr[i];
     if (t == 0) {
         si[SI_R] = R;
@@ -424,14 +429,14 @@ __device__ __forceinline__ uint32_t section_bytes(const uint4 &lo, const uint4 &
 }
 
 __global__ void __launch_bounds__(1024)
-k_block_layout(Ws ws, uint32_t nBlocks, uint32_t withHeader, uint64_t outCap)
+k_block_layout(Ws ws, uint32_t nBlocks, uint32_t headerLen, uint64_t outCap)
 {
     __shared__ unsigned long long warpSum[32];
     __shared__ unsigned long long running;
     __shared__ unsigned long long accSin, accSout, accTok, accMat;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        running = ws.counters[C_CURSOR] + (withHeader ? 10ull : 0ull);
+        running = ws.counters[C_CURSOR] + headerLen;
         accSin = accSout = accTok = accMat = 0;
     }
     __syncthreads();
@@ -1098,18 +1103,25 @@ k_encode_slow(Ws ws, uint32_t *__restrict__ out32)
 // headers: file header, record sizes, counters, serialised trees, raw bitmap byte
 // =========================================================================================
 __global__ void __launch_bounds__(128)
-k_headers(Ws ws, uint8_t *__restrict__ out, uint32_t nBlocks, uint32_t withHeader,
-          uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor)
+k_headers(Ws ws, uint8_t *__restrict__ out, uint32_t nBlocks, uint32_t flags,
+          uint64_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor)
 {
     if (ws.totals[TOT_ERR]) return;
     const int lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nBlocks) return;
-    if (b == 0 && withHeader && lane == 0) {
+    if (b == 0 && (flags & FCX_WITH_HEADER) && lane == 0) {
         uint8_t *h = out + batchStartCursor;              // mc:101-109 packed header, rewritten at mc:4128-4129
-        h[0] = 'F'; h[1] = 'C'; h[2] = 'X'; h[3] = '7';
-        st_u32_bytes(h + 4, hdrTotalBytes);               // uInt32 cmp_before_bytes (wraps)
-        h[8] = (uint8_t)hdrBlocks; h[9] = (uint8_t)(hdrBlocks >> 8);   // uInt16 block_num (wraps)
+        h[0] = 'F'; h[1] = 'C'; h[2] = 'X';
+        if (flags & FCX_FORMAT_X9) {                      // opt-in format: u64 byte count, u32 block count
+            h[3] = '9';
+            st_u32_bytes(h + 4, (uint32_t)hdrTotalBytes); st_u32_bytes(h + 8, (uint32_t)(hdrTotalBytes >> 32));
+            st_u32_bytes(h + 12, hdrBlocks);
+        } else {
+            h[3] = '7';
+            st_u32_bytes(h + 4, (uint32_t)hdrTotalBytes);     // uInt32 cmp_before_bytes (wraps)
+            h[8] = (uint8_t)hdrBlocks; h[9] = (uint8_t)(hdrBlocks >> 8);   // uInt16 block_num (wraps)
+        }
     }
     const unsigned long long off = ws.blkOff[b];
     const uint32_t *m = ws.meta + (size_t)b * M_WORDS;
@@ -1148,8 +1160,8 @@ void huff_init()
     cudaFuncSetAttribute(k_encode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncWSmem));
 }
 
-int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
-                      uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
+int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t flags,
+                      uint64_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
                       cudaStream_t st, void (*mark)(void *, int), void *markArg)
 {
     const uint32_t nSeg = nBlocks * 4;
@@ -1160,10 +1172,10 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     if (mark) mark(markArg, 2);
     k_hist<<<numSM * 8, 256, 0, st>>>(ws); launches++;
     if (mark) mark(markArg, 3);
-    k_tree<<<nSeg, 256, 0, st>>>(ws, nSeg); launches++;
+    k_tree<<<nSeg, 256, 0, st>>>(ws, nSeg, (flags & FCX_FORMAT_X9) ? 1u : 0u); launches++;
     if (mark) mark(markArg, 4);
     k_chunk_bits<<<numSM * 4, 256, 0, st>>>(ws); launches++;
-    k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, withHeader, outCap); launches++;
+    k_block_layout<<<1, 1024, 0, st>>>(ws, nBlocks, (flags & FCX_WITH_HEADER) ? ((flags & FCX_FORMAT_X9) ? FCX_X9_HEADER_BYTES : FCX_HEADER_BYTES) : 0u, outCap); launches++;
     // k_encode_w writes a sub-chunk that is too dense for its stage itself; only long-code streams go to k_encode_slow
     k_seg_scan<<<(nSeg + 7) / 8, 256, 0, st>>>(ws, nSeg); launches++;
     const uint32_t encGrid = (uint32_t)std::min(numSM * EW_CTAS, (int)kMaxEncCtas);
@@ -1174,7 +1186,7 @@ int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t out
     if (mark) mark(markArg, 6);
     k_encode_slow<<<numSM * 2, ENC_THREADS, 0, st>>>(ws, reinterpret_cast<uint32_t *>(out)); launches++;
     if (mark) mark(markArg, 7);
-    k_headers<<<(nBlocks + 3) / 4, 128, 0, st>>>(ws, out, nBlocks, withHeader, hdrTotalBytes, hdrBlocks, batchStartCursor);
+    k_headers<<<(nBlocks + 3) / 4, 128, 0, st>>>(ws, out, nBlocks, flags, hdrTotalBytes, hdrBlocks, batchStartCursor);
     launches++;
     if (mark) mark(markArg, 8);
     return launches;

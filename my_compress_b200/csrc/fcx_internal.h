@@ -17,12 +17,12 @@ int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32
 void parse_init();
 // fcx_huff.cu
 void huff_init();
-int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t withHeader,
-                      uint32_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
+int launch_huff_stage(const Ws &ws, uint32_t nBlocks, uint8_t *out, uint64_t outCap, uint32_t flags,   // FCX_WITH_HEADER | FCX_FORMAT_X9
+                      uint64_t hdrTotalBytes, uint32_t hdrBlocks, uint64_t batchStartCursor, int numSM,
                       cudaStream_t st, void (*mark)(void *, int), void *markArg);
 // fcx_decode.cu
 int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out,
-                  uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st);
+                  uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st, bool x9 = false);
 size_t decode_scratch_per_block();
 void decode_init();
 

@@ -174,7 +174,9 @@ uint32_t fcxo_huffman_codes(uint32_t R, const uint32_t child[510], uint64_t bits
 /* ------------------------------------------------------------------ */
 /* A.4 Huffman section (mc:987-1104)                                   */
 /* ------------------------------------------------------------------ */
-uint32_t fcxo_huffman_section(const uint8_t *src, uint32_t S, uint8_t *out)
+/* x9: the opt-in FCX9 format (include/fcx.h) -- a section without tree nodes names its one symbol after the zero
+ * count.  This is the only place the two payload formats differ on the encoder side. */
+static uint32_t huffman_section_fmt(const uint8_t *src, uint32_t S, uint8_t *out, int x9)
 {
     if (!src || !out || S == 0) return 0;            /* mc:989-990 */
     uint32_t w[256] = {0};
@@ -185,6 +187,7 @@ uint32_t fcxo_huffman_section(const uint8_t *src, uint32_t S, uint8_t *out)
     uint32_t mapB = (2 * Tn + 7) / 8;                /* mc:1024-1026 */
     uint8_t *q = out;
     *q++ = (uint8_t)Tn;
+    if (x9 && Tn == 0) *q++ = src[0];                /* FCX9: the symbol FCX7 drops */
     memset(q, 0, mapB);
     for (uint32_t j = 0; j < Tn; j++)
         for (uint32_t side = 0; side < 2; side++)
@@ -211,6 +214,8 @@ uint32_t fcxo_huffman_section(const uint8_t *src, uint32_t S, uint8_t *out)
     q += (size_t)W * 4;
     return (uint32_t)(q - out);
 }
+
+uint32_t fcxo_huffman_section(const uint8_t *src, uint32_t S, uint8_t *out) { return huffman_section_fmt(src, S, out, 0); }
 
 /* ------------------------------------------------------------------ */
 /* A.5 Golomb-Rice (mc:258-304), p packing (mc:1292-1313)              */
@@ -248,7 +253,7 @@ uint32_t fcxo_combine_bits(const uint32_t *v, uint32_t cnt, uint32_t bits, uint8
 /* ------------------------------------------------------------------ */
 /* A.6 block payload (mc:2115-2253) and container (mc:4073-4136)       */
 /* ------------------------------------------------------------------ */
-uint32_t fcxo_serialize_block(const uint32_t *p, const uint32_t *l, const uint8_t *c, uint32_t T, uint8_t *out)
+static uint32_t serialize_block_fmt(const uint32_t *p, const uint32_t *l, const uint8_t *c, uint32_t T, uint8_t *out, int x9)
 {
     uint8_t *q = out;
     put_u32(q, T); q += 4;                                         /* mc:2137-2139 */
@@ -256,11 +261,11 @@ uint32_t fcxo_serialize_block(const uint32_t *p, const uint32_t *l, const uint8_
     uint32_t mapB = (T + 7) / 8;
     uint8_t *bm = (uint8_t *)calloc(mapB ? mapB : 1, 1);
     for (uint32_t t = 0; t < T; t++) if (l[t] == 0) bm[t >> 3] |= (uint8_t)(1u << (t & 7));
-    if (mapB > 1) q += fcxo_huffman_section(bm, mapB, q);
+    if (mapB > 1) q += huffman_section_fmt(bm, mapB, q, x9);
     else { memcpy(q, bm, mapB); q += mapB; }                       /* mc:2104-2107: raw */
     free(bm);
     /* c stream */
-    q += fcxo_huffman_section(c, T, q);                            /* mc:2178 */
+    q += huffman_section_fmt(c, T, q, x9);                         /* mc:2178 */
     /* matches */
     uint32_t *mp = (uint32_t *)malloc(sizeof(uint32_t) * (T ? T : 1));
     uint32_t *ml = (uint32_t *)malloc(sizeof(uint32_t) * (T ? T : 1));
@@ -269,27 +274,35 @@ uint32_t fcxo_serialize_block(const uint32_t *p, const uint32_t *l, const uint8_
     put_u32(q, Pc); q += 4;                                        /* mc:2186-2188 */
     uint8_t *pk = (uint8_t *)malloc((size_t)(FCXO_P_BITS * Pc) / 8 + 1);
     uint32_t pkB = fcxo_combine_bits(mp, Pc, FCXO_P_BITS, pk);     /* mc:2193-2195 */
-    q += fcxo_huffman_section(pk, pkB, q);                         /* mc:2207 */
+    q += huffman_section_fmt(pk, pkB, q, x9);                      /* mc:2207 */
     free(pk);
     uint32_t *gw = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)Pc * 3 + 1));
     uint32_t G = fcxo_golomb_encode(ml, Pc, gw);                   /* mc:2221 */
     put_u32(q, G); q += 4;                                         /* mc:2225-2227 */
-    q += fcxo_huffman_section((const uint8_t *)gw, G * 4, q);      /* mc:2238 (emits nothing when G==0) */
+    q += huffman_section_fmt((const uint8_t *)gw, G * 4, q, x9);   /* mc:2238 (emits nothing when G==0) */
     free(gw); free(mp); free(ml);
     return (uint32_t)(q - out);
 }
 
-uint32_t fcxo_compress_block(const uint8_t *x, uint32_t n, uint8_t *out)
+uint32_t fcxo_serialize_block(const uint32_t *p, const uint32_t *l, const uint8_t *c, uint32_t T, uint8_t *out)
+{
+    return serialize_block_fmt(p, l, c, T, out, 0);
+}
+
+static uint32_t compress_block_fmt(const uint8_t *x, uint32_t n, uint8_t *out, int x9)
 {
     if (!x || !out) return 0;                                      /* mc:2122-2123 */
     uint32_t *p = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
     uint32_t *l = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
     uint8_t *c = (uint8_t *)malloc(n ? n : 1);
     uint32_t T = fcxo_lz77_parse(x, n, p, l, c);
-    uint32_t bytes = fcxo_serialize_block(p, l, c, T, out);
+    uint32_t bytes = serialize_block_fmt(p, l, c, T, out, x9);
     free(p); free(l); free(c);
     return bytes;
 }
+
+uint32_t fcxo_compress_block(const uint8_t *x, uint32_t n, uint8_t *out) { return compress_block_fmt(x, n, out, 0); }
+uint32_t fcxo_compress_block_x9(const uint8_t *x, uint32_t n, uint8_t *out) { return compress_block_fmt(x, n, out, 1); }
 
 uint64_t fcxo_compress_bound(uint64_t n)
 {
@@ -298,17 +311,33 @@ uint64_t fcxo_compress_bound(uint64_t n)
     return 10 + nb * (4 + 12 + 4 * 583 + 8) + n + n / 8 + 64;
 }
 
-uint64_t fcxo_compress_blocks(const uint8_t *x, uint64_t n, uint32_t b0, uint32_t b1, uint8_t *out)
+static uint64_t compress_blocks_fmt(const uint8_t *x, uint64_t n, uint32_t b0, uint32_t b1, uint8_t *out, int x9)
 {
     uint8_t *q = out;
     for (uint32_t b = b0; b < b1; b++) {
         uint64_t off = (uint64_t)b * FCXO_BLOCK_BYTES;
         uint32_t len = (uint32_t)((n - off) < FCXO_BLOCK_BYTES ? (n - off) : FCXO_BLOCK_BYTES);
-        uint32_t sz = fcxo_compress_block(x + off, len, q + 4);
+        uint32_t sz = compress_block_fmt(x + off, len, q + 4, x9);
         put_u32(q, sz);                                            /* mc:4111 */
         q += 4 + sz;
     }
     return (uint64_t)(q - out);
+}
+
+uint64_t fcxo_compress_blocks(const uint8_t *x, uint64_t n, uint32_t b0, uint32_t b1, uint8_t *out)
+{
+    return compress_blocks_fmt(x, n, b0, b1, out, 0);
+}
+
+/* FCX9 container: 'F','C','X','9' | u64 bytes | u32 blocks | FCX9 records (include/fcx.h) */
+uint64_t fcxo_compress_file_x9(const uint8_t *x, uint64_t n, uint8_t *out)
+{
+    uint64_t nb = (n + FCXO_BLOCK_BYTES - 1) / FCXO_BLOCK_BYTES;
+    uint32_t nb32 = (uint32_t)nb;
+    out[0] = 'F'; out[1] = 'C'; out[2] = 'X'; out[3] = '9';
+    memcpy(out + 4, &n, 8);
+    memcpy(out + 12, &nb32, 4);
+    return 16 + compress_blocks_fmt(x, n, 0, nb32, out + 16, 1);
 }
 
 uint64_t fcxo_compress_file(const uint8_t *x, uint64_t n, uint8_t *out)
@@ -336,9 +365,17 @@ static uint32_t rd_u32(rd_t *r)
 }
 
 /* mc:1107-1187 + mc:930-984.  Decodes cnt symbols into out (pre-zeroed by caller). */
-static int huff_section_decode(rd_t *r, uint8_t *out, uint32_t cnt)
+static int huff_section_decode(rd_t *r, uint8_t *out, uint32_t cnt, int x9)
 {
     uint32_t Tn = rd_u8(r);
+    if (x9 && Tn == 0) {                             /* FCX9: the named symbol, then W (= 0) */
+        uint8_t sym = rd_u8(r);
+        uint32_t W0 = rd_u32(r);
+        if (r->pos + (uint64_t)W0 * 4 > r->n + (2u << 20)) return -1;
+        r->pos += (uint64_t)W0 * 4;
+        memset(out, sym, cnt);
+        return 0;
+    }
     uint32_t mapB = (2 * Tn + 7) / 8;
     uint8_t map[64] = {0}, pair[510];
     for (uint32_t k = 0; k < mapB; k++) map[k] = rd_u8(r);
@@ -367,7 +404,7 @@ static int huff_section_decode(rd_t *r, uint8_t *out, uint32_t cnt)
     return 0;
 }
 
-uint32_t fcxo_decompress_block(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap)
+static uint32_t decompress_block_fmt(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap, int x9)
 {
     rd_t r = { payload, nbytes, 0 };
     uint32_t T = rd_u32(&r);
@@ -377,18 +414,18 @@ uint32_t fcxo_decompress_block(const uint8_t *payload, uint32_t nbytes, uint8_t 
     uint8_t *cs = (uint8_t *)calloc(T + 1, 1);
     uint32_t rc = UINT32_MAX;
     uint8_t *pk = NULL, *gb = NULL; uint32_t *ml = NULL;
-    if (mapB > 1) { if (huff_section_decode(&r, bm, mapB)) goto done; }
+    if (mapB > 1) { if (huff_section_decode(&r, bm, mapB, x9)) goto done; }
     else for (uint32_t k = 0; k < mapB; k++) bm[k] = rd_u8(&r);      /* mc:2277-2280 */
-    if (huff_section_decode(&r, cs, T)) goto done;                   /* mc:2283 */
+    if (huff_section_decode(&r, cs, T, x9)) goto done;               /* mc:2283 */
     uint32_t Pc = rd_u32(&r);
     if (Pc > (1u << 20)) goto done;
     uint32_t pkB = (FCXO_P_BITS * Pc) / 8 + 1;
     pk = (uint8_t *)calloc(pkB + 4, 1);
-    if (huff_section_decode(&r, pk, pkB)) goto done;                 /* mc:2292 */
+    if (huff_section_decode(&r, pk, pkB, x9)) goto done;             /* mc:2292 */
     uint32_t G = rd_u32(&r);
     if (G > (1u << 20)) goto done;
     gb = (uint8_t *)calloc((size_t)G * 4 + 4, 1);
-    if (huff_section_decode(&r, gb, G * 4)) goto done;               /* mc:2308 (G==0: reads zeros, B8) */
+    if (G || !x9) { if (huff_section_decode(&r, gb, G * 4, x9)) goto done; }   /* mc:2308 (FCX7, G==0: reads zeros, B8; FCX9: no section) */
     /* Golomb decode (mc:309-358): stops after Pc values */
     ml = (uint32_t *)calloc(Pc + 1, sizeof(uint32_t));
     {
@@ -432,14 +469,26 @@ done:
     return rc;
 }
 
+uint32_t fcxo_decompress_block(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap)
+{
+    return decompress_block_fmt(payload, nbytes, out, out_cap, 0);
+}
+uint32_t fcxo_decompress_block_x9(const uint8_t *payload, uint32_t nbytes, uint8_t *out, uint32_t out_cap)
+{
+    return decompress_block_fmt(payload, nbytes, out, out_cap, 1);
+}
+
 uint64_t fcxo_decompress_file(const uint8_t *file, uint64_t nbytes, uint8_t *out, uint64_t out_cap)
 {
     if (nbytes < 10) return UINT64_MAX;
     if (file[0] != 'F' || file[1] != 'C' || file[2] != 'X') return UINT64_MAX;   /* mc:4146-4152 */
-    if (file[3] != '7' && file[3] != '8') return UINT64_MAX;                      /* mc:4153-4164: '7' = lz77, '8' = lz78 */
-    const int lz78 = file[3] == '8';
-    uint16_t nb; memcpy(&nb, file + 8, 2);
-    uint64_t pos = 10, cur = 0;
+    if (file[3] != '7' && file[3] != '8' && file[3] != '9') return UINT64_MAX;    /* mc:4153-4164: '7' = lz77, '8' = lz78; '9' = opt-in */
+    const int lz78 = file[3] == '8', x9 = file[3] == '9';
+    uint32_t nb; uint64_t pos = 10, cur = 0;
+    if (x9) {
+        if (nbytes < 16) return UINT64_MAX;
+        memcpy(&nb, file + 12, 4); pos = 16;
+    } else { uint16_t nb16; memcpy(&nb16, file + 8, 2); nb = nb16; }
     for (uint32_t b = 0; b < nb; b++) {
         if (pos + 4 > nbytes) return UINT64_MAX;
         uint32_t sz = get_u32(file + pos); pos += 4;
@@ -447,7 +496,7 @@ uint64_t fcxo_decompress_file(const uint8_t *file, uint64_t nbytes, uint8_t *out
         uint64_t room = out_cap - cur;
         const uint32_t room32 = room > 0xffffffffu ? 0xffffffffu : (uint32_t)room;
         uint32_t got = lz78 ? fcxo_decompress_block_lz78(file + pos, sz, out + cur, room32)
-                            : fcxo_decompress_block(file + pos, sz, out + cur, room32);
+                            : decompress_block_fmt(file + pos, sz, out + cur, room32, x9);
         if (got == UINT32_MAX) return UINT64_MAX;
         cur += got; pos += sz;
     }
@@ -648,7 +697,7 @@ uint32_t fcxo_decompress_block_lz78(const uint8_t *payload, uint32_t nbytes, uin
         const uint64_t pos0 = r.pos;
         r.pos += T;
         cs = (uint8_t *)calloc(T, 1);
-        if (huff_section_decode(&r, cs, T) < 0) goto done;
+        if (huff_section_decode(&r, cs, T, 0) < 0) goto done;
         start = (uint32_t *)malloc((size_t)T * sizeof(uint32_t));
         len = (uint32_t *)malloc((size_t)T * sizeof(uint32_t));
         uint32_t cur = 0;

@@ -177,6 +177,13 @@ class Oracle(_Codec):
         lib.fcxo_longest_match.argtypes = [u8p, C.c_uint32, C.c_uint32, u32p, u32p]
         lib.fcxo_compress_file_lz78.restype = C.c_uint64
         lib.fcxo_compress_file_lz78.argtypes = [u8p, C.c_uint64, u8p]
+        # FCX9 (scope row f-4): the opt-in format
+        lib.fcxo_compress_block_x9.restype = C.c_uint32
+        lib.fcxo_compress_block_x9.argtypes = [u8p, C.c_uint32, u8p]
+        lib.fcxo_decompress_block_x9.restype = C.c_uint32
+        lib.fcxo_decompress_block_x9.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32]
+        lib.fcxo_compress_file_x9.restype = C.c_uint64
+        lib.fcxo_compress_file_x9.argtypes = [u8p, C.c_uint64, u8p]
 
     def huffman_tree(self, weights):
         w = np.ascontiguousarray(weights, dtype=np.uint32)
@@ -221,6 +228,25 @@ class Oracle(_Codec):
 
     def compress_bound(self, n):
         return int(self.lib.fcxo_compress_bound(n))
+
+    def compress_block_x9(self, data):
+        x = _as_u8(data)
+        out = np.zeros(2 << 20, np.uint8)
+        k = self.lib.fcxo_compress_block_x9(_p8(x), len(x), _p8(out))
+        return out[:k].tobytes()
+
+    def decompress_block_x9(self, payload, cap=(1 << 20) + 8):
+        x = _as_u8(payload)
+        out = np.zeros(cap, np.uint8)
+        k = self.lib.fcxo_decompress_block_x9(_p8(x), len(x), _p8(out), cap)
+        return None if k == 0xFFFFFFFF else out[:k].tobytes()
+
+    def compress_file_x9(self, data):
+        x = _as_u8(data)
+        nb = (len(x) + (1 << 20) - 1) >> 20
+        out = np.zeros(16 + nb * (4 + (2 << 20)) + 64, np.uint8)
+        k = self.lib.fcxo_compress_file_x9(_p8(x if len(x) else np.zeros(1, np.uint8)), len(x), _p8(out))
+        return out[:k].tobytes()
 
     def compress_file_lz78(self, data):
         """FCX8 container (the reference CLI's `-c <anything but lz77>`)."""

@@ -49,8 +49,11 @@ def test_argument_errors(L):
     assert L.fcx_compress_block_lz77(out.ctypes.data, (1 << 20) + 1, out.ctypes.data, 64, C.byref(n32)) == -1
     bad = np.frombuffer(b"NOPE000000000000", np.uint8)
     assert L.fcx_decompress_lz77(bad.ctypes.data, len(bad), out.ctypes.data, 64, C.byref(n), 1) == -5   # mc:4146-4152
-    fcx9 = np.frombuffer(b"FCX9" + bytes(12), np.uint8)                 # '7' = lz77, '8' = lz78, nothing else (mc:4153-4164)
-    assert L.fcx_decompress_lz77(fcx9.ctypes.data, len(fcx9), out.ctypes.data, 64, C.byref(n), 1) == -5
+    fcx6 = np.frombuffer(b"FCX6" + bytes(12), np.uint8)                 # '7' = lz77, '8' = lz78 (mc:4153-4164), '9' = the opt-in format
+    assert L.fcx_decompress_lz77(fcx6.ctypes.data, len(fcx6), out.ctypes.data, 64, C.byref(n), 1) == -5
+    # FCX9 header whose block count contradicts its byte count: rejected before anything is sized from it
+    bad9 = np.frombuffer(b"FCX9" + (5).to_bytes(8, "little") + (0xFFFFFFFF).to_bytes(4, "little"), np.uint8)
+    assert L.fcx_decompress_lz77(bad9.ctypes.data, len(bad9), out.ctypes.data, 64, C.byref(n), 1) in (-5, -2)
 
 
 def test_context_batch_limit(L):
