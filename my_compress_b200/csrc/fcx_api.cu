@@ -134,8 +134,7 @@ extern "C" int fcx_ctx_create(fcx_ctx **out, int device, uint32_t maxBatchBlocks
     A(dalloc(c, &w.lenCode, B * kBlockBytes));
     A(dalloc(c, &w.dist, B * kBlockBytes));
     for (int k = 0; k < 4; k++) { w.strmStride[k] = seg_stride(k); A(dalloc(c, &w.strm[k], B * seg_stride(k))); }
-    A(dalloc(c, &w.parseExit, B * kParseTilesPerBlock * kParseEntries));
-    A(dalloc(c, &w.tileEntry, B * kParseTilesPerBlock));
+    A(dalloc(c, &w.tileExit, B * kParseTilesPerBlock));
     A(dalloc(c, &w.tileState, B * kParseTilesPerBlock));
     A(dalloc(c, &w.blkLen, B));
     A(dalloc(c, &w.meta, B * M_WORDS));

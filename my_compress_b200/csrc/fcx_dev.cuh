@@ -57,8 +57,7 @@ struct Ws {
     uint16_t *dist;       // [maxBlocks][1 MiB]
     uint8_t *strm[4];     // [maxBlocks][stride]
     uint32_t strmStride[4];
-    uint16_t *parseExit;  // [maxBlocks][256 tiles][258] exit offset (0..257) of a tile per entry offset
-    uint16_t *tileEntry;  // [maxBlocks][256] offset at which the chain enters each tile
+    uint32_t *tileExit;   // [maxBlocks][256] bit 31 = known | offset at which the chain enters the NEXT tile (fcx_parse.cu)
     unsigned long long *tileState;   // [maxBlocks][256] look-back status word of each parse tile (fcx_parse.cu)
     uint32_t *blkLen;     // [maxBlocks]
     uint32_t *meta;       // [maxBlocks][M_WORDS]

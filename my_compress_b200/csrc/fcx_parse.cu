@@ -5,23 +5,29 @@
 // (mc:1292-1313) and golomb_rice_encode (mc:258-304).  Input is the per-position (len, dist)
 // table of k_match; output is the four byte streams the Huffman stage encodes.
 //
-// The parse is a dependent chain next(i) = i + len(i) + 1 with steps of 1..258.  It runs as a
-// device-wide scan over tiles of 4096 positions instead of a serial walk:
-//   k_parse_exits   every tile, for each of the 258 positions a chain can enter it at, the
-//                   position it leaves at (exit function of the tile)
-//   k_parse_entries per block, composes the exit functions tile by tile -> entry of each tile
-//   k_parse_emit    every tile walks its part of the chain ONCE: counts its tokens, matches and
-//                   Golomb bits, publishes them, packs c bytes, flag bits, 11-bit distances and
-//                   Golomb codes into shared memory, learns the rank of its first token from the
-//                   counts the tiles before it have published (one 64-bit status word per tile:
-//                   the device-wide scan of the parse, overlapped with the packing), and copies
-//                   the packed bits to their final bit positions
+// The parse is a dependent chain next(i) = i + len(i) + 1 with steps of 1..258.  It runs as ONE kernel over
+// tiles of 4096 positions (k_parse), every tile doing three things:
+//   exit     for each of the 258 offsets a chain can enter the tile at, the offset at which it enters the next
+//            one (the tile's exit function, from the jump tables below).  Chains that start at different offsets
+//            fall into step after a few tokens, so the function is almost always CONSTANT: the tile then
+//            publishes its exit at once, without knowing its own entry.  Otherwise it waits for the exit of the
+//            tile before it (one word per tile, a chain of waits only through runs of such tiles -- e.g. a block
+//            of one repeated byte, whose 258-byte tokens never merge) and publishes exit(entry).
+//   counts   with its entry known the tile walks its part of the chain: tokens, matches, Golomb bits; it
+//            publishes them and learns the rank of its first token from the counts of the tiles before it (one
+//            64-bit word per tile, all read at once: the device-wide scan of the parse)
+//   emit     c bytes, flag bits, 11-bit distances and Golomb codes are packed in shared memory during that wait
+//            and copied to their final bit positions
+// CTAs are numbered block-first (blockIdx.x = block, blockIdx.y = tile): the CTAs resident at any time are the
+// same few tiles of MANY blocks, so the tile a CTA waits for was dispatched a whole row of CTAs earlier and has
+// normally finished; a CTA only ever waits for lower-numbered ones.
 // Inside a tile the chain is resolved by a three-level jump table:
 //   J1[i] = first chain position at or beyond the end of i's 16-position mini-tile
 //   J2[i] = first chain position at or beyond the end of i's 256-position mid-tile
 // both built by backward sweeps (16 dependent steps each, all threads busy); 16 hops then
 // give the entry of every mid-tile, 16 more the entry of every mini-tile, and each thread
-// walks its own mini-tile (<= 16 tokens).
+// walks its own mini-tile (<= 16 tokens).  A mini-tile without a match (most of them on incompressible
+// input) skips its sweep and its walks: its jumps, counts, flag bits and c bytes are known from its entry.
 #include "fcx_dev.cuh"
 
 namespace fcx {
@@ -53,14 +59,23 @@ __device__ __forceinline__ bool tile_has_match(const uint8_t *lcG, int tb)
     return __syncthreads_or((v.x | v.y | v.z | v.w) != 0u) != 0;
 }
 
-// stage the tile's len codes and build J1 / J2 (ends with a __syncthreads)
-__device__ __forceinline__ void build_jumps(JumpSmem &sm, const uint8_t *lcG, int tb, int limit)
+// stage the tile's len codes and build J1 / J2 (ends with a __syncthreads).  Returns whether this thread's own
+// mini-tile (positions 16 tid .. 16 tid + 15) holds no match.
+__device__ __forceinline__ bool build_jumps(JumpSmem &sm, const uint8_t *lcG, int tb, int limit)
 {
     const int tid = threadIdx.x;
     const uint4 v = reinterpret_cast<const uint4 *>(lcG + tb)[tid];
     reinterpret_cast<uint4 *>(sm.lc)[tid] = v;
-    {   // (a) mini-tile backward sweep
-        const int base = tid * 16;
+    const int base = tid * 16, pad = 2 * tid;              // jphys(i) = i + pad for every i of this thread's mini-tile
+    // codes beyond the block's end are stale (k_match writes none there): they count as literals
+    const bool plain = (v.x | v.y | v.z | v.w) == 0u || base >= limit;
+    if (plain) {
+        // (a') nothing but literals: every position leads to the end of the mini-tile
+        uint32_t *w = reinterpret_cast<uint32_t *>(sm.J1) + 9 * tid;     // (base + pad) / 2: 18 tid is even
+        const uint32_t two = (uint32_t)(base + 16) * 0x10001u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = two;
+    } else {   // (a) mini-tile backward sweep
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 15; j >= 0; j--) {
@@ -68,8 +83,8 @@ __device__ __forceinline__ void build_jumps(JumpSmem &sm, const uint8_t *lcG, in
             const uint32_t code = (w[j >> 2] >> ((j & 3) * 8)) & 0xFF;
             const int len = (i < limit) ? code_len(code) : 0;
             const int nx = i + len + 1;
-            const uint16_t val = (nx >= base + 16) ? (uint16_t)nx : sm.J1[jphys(nx)];
-            sm.J1[jphys(i)] = val;
+            const uint16_t val = (nx >= base + 16) ? (uint16_t)nx : sm.J1[nx + pad];    // nx stays in this mini-tile
+            sm.J1[i + pad] = val;
         }
     }
     __syncthreads();
@@ -77,14 +92,15 @@ __device__ __forceinline__ void build_jumps(JumpSmem &sm, const uint8_t *lcG, in
         const int M = tid >> 4, j = tid & 15;
         const int midEnd = (M + 1) * 256;
         for (int m = 15; m >= 0; m--) {
-            const int i = M * 256 + m * 16 + j;
-            const int a = sm.J1[jphys(i)];
+            const int ip = M * 256 + m * 16 + j + 2 * (M * 16 + m);         // jphys of position M*256 + m*16 + j
+            const int a = sm.J1[ip];
             const uint16_t val = (a >= midEnd) ? (uint16_t)a : sm.J2[jphys(a)];
-            sm.J2[jphys(i)] = val;
+            sm.J2[ip] = val;
             __syncwarp();
         }
     }
     __syncthreads();
+    return plain;
 }
 
 // entries of the 16 mid-tiles and 256 mini-tiles for a known tile entry (ends with a __syncthreads)
@@ -110,56 +126,6 @@ __device__ __forceinline__ void resolve_entries(JumpSmem &sm, int entry)
     __syncthreads();
 }
 
-// ---- 1: exit function of every tile ----------------------------------------------------------
-__global__ void __launch_bounds__(PT_THREADS)
-k_parse_exits(const uint32_t *__restrict__ blkLen, const uint8_t *__restrict__ lenCode, Ws ws)
-{
-    __shared__ JumpSmem sm;
-    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    const int n = (int)blkLen[b];
-    const int tb = tile * PT;
-    if (tb >= n) return;
-    uint16_t *ex = ws.parseExit + ((size_t)b * kParseTilesPerBlock + tile) * PT_ENTRIES;
-    if (!tile_has_match(lenCode + (size_t)b * kBlockBytes, tb)) {     // codes past n are never non-zero (k_match writes none)
-        for (int e0 = tid; e0 < PT_ENTRIES; e0 += PT_THREADS) ex[e0] = 0;
-        return;
-    }
-    build_jumps(sm, lenCode + (size_t)b * kBlockBytes, tb, min(PT, n - tb));
-    for (int e0 = tid; e0 < PT_ENTRIES; e0 += PT_THREADS) {
-        int e = e0;
-        while (e < PT) e = sm.J2[jphys(e)];            // <= 16 hops, one mid-tile each
-        ex[e0] = (uint16_t)(e - PT);
-    }
-}
-
-// ---- 2: compose them along each block -----------------------------------------------------------
-// The composition is a chain of 256 dependent look-ups.  Out of global memory that is 256
-// exposed L2 latencies per block, so the CTA first pulls the block's whole exit table (129 KiB)
-// into shared memory with coalesced 16-byte loads and thread 0 then hops through it there.
-constexpr int PE_THREADS = 512;
-constexpr int PE_TABLE = kParseTilesPerBlock * PT_ENTRIES;     // 66048 entries
-__global__ void __launch_bounds__(PE_THREADS)
-k_parse_entries(const uint32_t *__restrict__ blkLen, Ws ws)
-{
-    extern __shared__ __align__(16) uint16_t exS[];
-    const uint32_t b = blockIdx.x;
-    const int n = (int)blkLen[b];
-    const int nTiles = (n + PT - 1) / PT;
-    const uint16_t *ex = ws.parseExit + (size_t)b * PE_TABLE;
-    const int nVec = (nTiles * PT_ENTRIES * 2 + 15) / 16;       // table rows are 516 bytes: the block's table is contiguous
-    for (int v = threadIdx.x; v < nVec; v += PE_THREADS)
-        reinterpret_cast<uint4 *>(exS)[v] = reinterpret_cast<const uint4 *>(ex)[v];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint16_t *en = ws.tileEntry + (size_t)b * kParseTilesPerBlock;
-        uint32_t e = 0;
-        for (int t = 0; t < nTiles; t++) {
-            en[t] = (uint16_t)e;
-            e = exS[t * PT_ENTRIES + e];
-        }
-    }
-}
-
 // walk of one mini-tile: counts
 __device__ __forceinline__ void walk_count(const uint8_t *lcb, int e0, int hi, uint32_t &tok, uint32_t &mat, uint32_t &gb)
 {
@@ -181,6 +147,8 @@ struct EmitSmem {
     uint32_t pbits[368];
     uint32_t gbits[128];
     unsigned long long base;              // look-back result: packed exclusive ranks of the tile's first token
+    uint16_t exitOf[PT_ENTRIES + 6];      // the tile's exit function (only consulted when it is not constant)
+    uint32_t exit0, entry;
 };
 
 // One status word per tile (ws.tileState, zeroed per launch): ready << 62 | Golomb bits << 40 | matches << 21 | tokens.
@@ -205,11 +173,26 @@ __device__ __forceinline__ unsigned long long ts_load(const unsigned long long *
     return v;
 }
 
+// One exit word per tile (ws.tileExit, zeroed per launch): bit 31 = known, low bits = the offset at which the
+// block's chain enters the NEXT tile.
+__device__ __forceinline__ void exit_publish(uint32_t *row, int tile, uint32_t exitOff)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(row + tile), "r"(0x80000000u | exitOff) : "memory");
+}
+__device__ __forceinline__ uint32_t exit_wait(const uint32_t *row, int tile)
+{
+    uint32_t v;
+    do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(row + tile) : "memory");
+    } while (!(v & 0x80000000u));
+    return v & 0x7FFFFFFFu;
+}
+
 // Ranks by one warp (all 32 lanes): sum of the counts of tiles 0..tile-1 of this block.  Every tile publishes its own
 // counts as soon as it knows them (before it packs its tokens), so by the time a tile asks, the words of the tiles
 // before it are usually all there: lane j reads words j, j + 32, ... (at most eight, all loads in flight at once) and
-// only spins on the ones not yet written.  Tiles of a block have consecutive CTA numbers (blockIdx.x runs fastest)
-// and a CTA only ever waits for lower-numbered ones, which were dispatched before it.
+// only spins on the ones not yet written.  A CTA only ever waits for lower-numbered ones (earlier tiles of its
+// block), which were dispatched before it.
 __device__ __forceinline__ unsigned long long tile_lookback(const unsigned long long *row, int tile, int lane)
 {
     static_assert(kParseTilesPerBlock == 256, "eight words per lane");
@@ -279,11 +262,11 @@ __device__ __forceinline__ void flush_bits(uint32_t *gstream, const uint32_t *bu
 }
 
 __global__ void __launch_bounds__(PT_THREADS)
-k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
-             const uint8_t *__restrict__ lenCode, const uint16_t *__restrict__ dist, Ws ws)
+k_parse(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
+        const uint8_t *__restrict__ lenCode, const uint16_t *__restrict__ dist, Ws ws)
 {
     __shared__ EmitSmem sm;
-    const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;   // block-first numbering
     const int n = (int)blkLen[b];
     const int tb = tile * PT;
     if (tb >= n) return;
@@ -291,11 +274,12 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     const int limit = min(PT, n - tb);
     const uint8_t *x = in + (size_t)b * kBlockBytes;
     const uint16_t *dsG = dist + (size_t)b * kBlockBytes;
+    uint32_t *exitRow = ws.tileExit + (size_t)b * kParseTilesPerBlock;
     if (!tile_has_match(lenCode + (size_t)b * kBlockBytes, tb)) {
-        // every token is a literal: c = the bytes themselves, flags = a run of ones at the tile's token rank
-        const int entry = ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile];
-        const uint32_t tileTok = (uint32_t)max(limit - entry, 0);
-        // the tile's bytes travel to shared memory while warp 0 asks the tiles before this one for the token rank
+        // every token is a literal: the chain leaves at offset 0 whatever its entry, c = the bytes themselves,
+        // flags = a run of ones at the tile's token rank
+        if (tid == 0) exit_publish(exitRow, tile, 0u);
+        // the tile's bytes travel to shared memory while thread 0 asks the tile before this one for the entry
         {
             const int pos = tb + tid * 16;
             uint4 q;
@@ -309,12 +293,18 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
             }
             reinterpret_cast<uint4 *>(sm.xs)[tid] = q;
         }
-        if (tid == 0) publish_counts(ws, b, tile, ts_pack(tileTok, 0, 0));
         if (warp == 0) {
-            const unsigned long long r = tile_ranks(ws, b, tile, nTiles, lane, ts_pack(tileTok, 0, 0));
+            uint32_t e = 0;
+            if (lane == 0 && tile) e = exit_wait(exitRow, tile - 1);
+            e = __shfl_sync(0xFFFFFFFFu, e, 0);
+            const uint32_t cnt = (uint32_t)max(limit - (int)e, 0);
+            if (lane == 0) { sm.entry = e; publish_counts(ws, b, tile, ts_pack(cnt, 0, 0)); }
+            const unsigned long long r = tile_ranks(ws, b, tile, nTiles, lane, ts_pack(cnt, 0, 0));
             if (lane == 0) sm.base = r;
         }
         __syncthreads();
+        const int entry = (int)sm.entry;
+        const uint32_t tileTok = (uint32_t)max(limit - entry, 0);
         const uint32_t baseTok = ts_tok(sm.base);
         const uint8_t *src = reinterpret_cast<const uint8_t *>(sm.xs) + entry;
         uint8_t *cOut = ws.strm[1] + (size_t)b * ws.strmStride[1] + baseTok;
@@ -358,15 +348,42 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     for (int k = tid; k < PT / 32 + 4; k += PT_THREADS) sm.fbits[k] = 0;
     for (int k = tid; k < 368; k += PT_THREADS) sm.pbits[k] = 0;
     for (int k = tid; k < 128; k += PT_THREADS) sm.gbits[k] = 0;
-    build_jumps(sm.j, lenCode + (size_t)b * kBlockBytes, tb, limit);
-    resolve_entries(sm.j, ws.tileEntry[(size_t)b * kParseTilesPerBlock + tile]);
+    const bool plain = build_jumps(sm.j, lenCode + (size_t)b * kBlockBytes, tb, limit);
+
+    // ---- exit function: where does a chain entering at offset e leave?  <= 16 hops, one mid-tile each ----
+    {
+        int e = tid;
+        while (e < PT) e = sm.j.J2[jphys(e)];
+        sm.exitOf[tid] = (uint16_t)(e - PT);
+        if (tid == 0) sm.exit0 = (uint32_t)(e - PT);
+        bool same = true;
+        if (tid < PT_ENTRIES - PT_THREADS) {                   // entries 256, 257
+            int e2 = PT_THREADS + tid;
+            while (e2 < PT) e2 = sm.j.J2[jphys(e2)];
+            sm.exitOf[PT_THREADS + tid] = (uint16_t)(e2 - PT);
+            same = e2 == e;                                    // compared with the first entry below through e
+        }
+        __syncthreads();
+        same = same && (uint32_t)(e - PT) == sm.exit0;
+        const bool constant = __syncthreads_and(same) != 0;
+        // entry: the exit of the tile before this one.  A constant tile has told its successor already.
+        if (tid == 0) {
+            if (constant) exit_publish(exitRow, tile, sm.exit0);
+            const uint32_t en = tile ? exit_wait(exitRow, tile - 1) : 0u;
+            if (!constant) exit_publish(exitRow, tile, sm.exitOf[en]);
+            sm.entry = en;
+        }
+        __syncthreads();
+    }
+    resolve_entries(sm.j, (int)sm.entry);
 
     const uint8_t *lcb = reinterpret_cast<const uint8_t *>(sm.j.lc);
     const uint8_t *xsb = reinterpret_cast<const uint8_t *>(sm.xs);
     const int hi = min(tid * 16 + 16, limit);
     const int e0 = sm.j.miniEntry[tid];
     uint32_t myTok, myMat, myGb;
-    walk_count(lcb, e0, hi, myTok, myMat, myGb);
+    if (plain) { myTok = (uint32_t)max(hi - e0, 0); myMat = 0; myGb = 0; }      // literals only: one token per byte from the entry on
+    else walk_count(lcb, e0, hi, myTok, myMat, myGb);
     // CTA exclusive scan of (tok | mat<<16) and gb
     const uint32_t packed = myTok | (myMat << 16);
     uint32_t incP = packed, incG = myGb;
@@ -397,27 +414,32 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     const uint32_t tok0 = tokIdx, mat0 = matIdx;
     uint32_t flagReg = 0;
     unsigned long long pReg = 0;
-    for (int e = e0; e < hi;) {
-        const int len = code_len(lcb[e]);
-        sm.cbuf[tokIdx] = xsb[e + len];                                           // mc:1489: byte after the match
-        if (len == 0) {
-            flagReg |= 1u << (tokIdx - tok0);                                     // mc:2087-2089: bit set = literal
-        } else {
-            pReg |= (unsigned long long)dsG[tb + e] << (kPBits * (matIdx - mat0));  // mc:1301-1309
-            const uint32_t gp = gOff;
-            const int q = len >> 2;                                               // mc:267-269: q ones, 0, 2 remainder bits
-            if (q <= 29) {                                                        // whole code fits 32 bits
-                or_bits(sm.gbits, gp, ((1u << q) - 1u) | ((uint32_t)(len & 3) << (q + 1)), q + 3);
+    if (plain) {
+        for (uint32_t k = 0; k < myTok; k++) sm.cbuf[tok0 + k] = xsb[e0 + (int)k];
+        flagReg = (1u << myTok) - 1u;                                             // myTok <= 16
+    } else {
+        for (int e = e0; e < hi;) {
+            const int len = code_len(lcb[e]);
+            sm.cbuf[tokIdx] = xsb[e + len];                                           // mc:1489: byte after the match
+            if (len == 0) {
+                flagReg |= 1u << (tokIdx - tok0);                                     // mc:2087-2089: bit set = literal
             } else {
-                if (q > 32) { or_bits(sm.gbits, gp, 0xFFFFFFFFu, 32); or_bits(sm.gbits, gp + 32, 0xFFFFFFFFu >> (64 - q), q - 32); }
-                else or_bits(sm.gbits, gp, 0xFFFFFFFFu >> (32 - q), q);
-                or_bits(sm.gbits, gp + q + 1, (uint32_t)(len & 3), 2);
+                pReg |= (unsigned long long)dsG[tb + e] << (kPBits * (matIdx - mat0));  // mc:1301-1309
+                const uint32_t gp = gOff;
+                const int q = len >> 2;                                               // mc:267-269: q ones, 0, 2 remainder bits
+                if (q <= 29) {                                                        // whole code fits 32 bits
+                    or_bits(sm.gbits, gp, ((1u << q) - 1u) | ((uint32_t)(len & 3) << (q + 1)), q + 3);
+                } else {
+                    if (q > 32) { or_bits(sm.gbits, gp, 0xFFFFFFFFu, 32); or_bits(sm.gbits, gp + 32, 0xFFFFFFFFu >> (64 - q), q - 32); }
+                    else or_bits(sm.gbits, gp, 0xFFFFFFFFu >> (32 - q), q);
+                    or_bits(sm.gbits, gp + q + 1, (uint32_t)(len & 3), 2);
+                }
+                matIdx++;
+                gOff += (uint32_t)q + 3;
             }
-            matIdx++;
-            gOff += (uint32_t)q + 3;
+            tokIdx++;
+            e += len + 1;
         }
-        tokIdx++;
-        e += len + 1;
     }
     if (flagReg) or_bits(sm.fbits, tok0, flagReg, 16);
     if (matIdx > mat0) {
@@ -440,24 +462,20 @@ k_parse_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     flush_bits(reinterpret_cast<uint32_t *>(ws.strm[3] + (size_t)b * ws.strmStride[3]), sm.gbits, baseGb, tileG);
 }
 
-void parse_init()
-{
-    cudaFuncSetAttribute(k_parse_entries, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PE_TABLE * sizeof(uint16_t) + 16));
-}
+void parse_init() {}
 
 int launch_parse(const uint8_t *in, const uint32_t *blkLen, const Ws &ws, uint32_t nBlocks, uint32_t maxLen, cudaStream_t st)
 {
-    const dim3 grid((maxLen + PT - 1) / PT, nBlocks);
+    const dim3 grid(nBlocks, (maxLen + PT - 1) / PT);               // block-first: see the file comment
     // flag / distance / Golomb streams are assembled with OR: start from zero (also yields the
     // spare zero byte of the p stream and the zero padding of the last Golomb word)
     cudaMemsetAsync(ws.strm[0], 0, (size_t)nBlocks * ws.strmStride[0], st);
     cudaMemsetAsync(ws.strm[2], 0, (size_t)nBlocks * ws.strmStride[2], st);
     cudaMemsetAsync(ws.strm[3], 0, (size_t)nBlocks * ws.strmStride[3], st);
-    k_parse_exits<<<grid, PT_THREADS, 0, st>>>(blkLen, ws.lenCode, ws);
-    k_parse_entries<<<nBlocks, PE_THREADS, PE_TABLE * sizeof(uint16_t) + 16, st>>>(blkLen, ws);
     cudaMemsetAsync(ws.tileState, 0, (size_t)nBlocks * kParseTilesPerBlock * sizeof(unsigned long long), st);
-    k_parse_emit<<<grid, PT_THREADS, 0, st>>>(in, blkLen, ws.lenCode, ws.dist, ws);
-    return 3;
+    cudaMemsetAsync(ws.tileExit, 0, (size_t)nBlocks * kParseTilesPerBlock * sizeof(uint32_t), st);
+    k_parse<<<grid, PT_THREADS, 0, st>>>(in, blkLen, ws.lenCode, ws.dist, ws);
+    return 1;
 }
 
 } // namespace fcx
