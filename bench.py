@@ -502,7 +502,27 @@ def measure(rig, api, workload, steps, warmup, want_cpu_baseline):
     return res
 
 
+def bind_near_gpu(index):
+    """Pins this process to the host cores NVML reports as local to GPU `index`, so that its pinned buffers are
+    allocated on that NUMA node (what numactl would do for a production caller; eight ranks that all stage through
+    one socket share its memory and PCIe root).  Returns the number of cores, 0 if nothing was changed."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), (ncpu + 63) // 64)
+        cpus = [c for c in range(ncpu) if (words[c // 64] >> (c % 64)) & 1]
+        if cpus and hasattr(os, "sched_setaffinity"):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_ours(args, rank, world, local_rank):
+    near = bind_near_gpu(local_rank) if world > 1 else 0
     import torch
     import torch.distributed as dist
 
@@ -539,7 +559,7 @@ def run_ours(args, rank, world, local_rank):
                        "total_bytes": per_gpu * world, "block_bytes": BLOCK, "window": 2047,
                        "l2": "flushed between steps (512 MiB write, untimed)",
                        "partitioning": "rank r holds blocks [%d r, %d (r+1)) of the %d-block file; contiguous block ranges, no collective" % (nblocks, nblocks, nblocks * world),
-                       "seed": args.seed},
+                       "host_cores_bound_near_gpu": near, "seed": args.seed},
             "clocks": main["clocks"], "gpu_launches": main["gpu_launches"],
             "e2e": main["e2e"], "roofline": main["roofline"], "kernels": main["kernels"], "output": main["output"],
             "decode": main.get("decode"), "parity": main.get("parity"),
