@@ -9,7 +9,7 @@
 // One CTA owns a tile of 4096 positions and stages tile + 2048 bytes of history + 272 bytes
 // of look-ahead in shared memory.  The 6144-slot region is cut into six 1024-slot
 // sub-regions; warp w threads the positions of sub-region w into ASCENDING per-hash chains
-// (hash of the 3-byte gram) with __match_any_sync, walking its chunks from the top so that
+// (hash of the 3-byte gram) with a ballot-built lane mask per hash value, walking its chunks from the top so that
 // head[] ends up holding the lowest slot and up[] the next higher slot of the same hash;
 // head[] also carries the bucket population.
 // The six chains of a bucket are then linked into one ascending chain over the whole region
@@ -55,6 +55,10 @@ constexpr int MT_PER_THREAD = MT_TILE / MT_THREADS;   // 16
 constexpr int MT_PROBES = 64;                         // positions sampled per tile
 constexpr int MT_PROBE_CAP = 40;                      // probed matches are not followed beyond this
 constexpr int MT_LONG_MEAN = 12;                      // mean probed match length that switches a tile to lazy evaluation
+#ifndef FCX_MT_LAZY_SPLIT_LOG2
+#define FCX_MT_LAZY_SPLIT_LOG2 3
+#endif
+constexpr int MT_LAZY_SPLIT_LOG2 = FCX_MT_LAZY_SPLIT_LOG2;            // lazy mode: up to 2^this lanes per position in rounds with few positions
 constexpr int MT_SPEC_STRIDE = FCX_MT_SPEC_STRIDE;                    // lazy mode: a speculative chain starts every 32 positions
 constexpr uint32_t MT_NONE = 0xFFFF;
 constexpr int MT_BINS = 32;
@@ -101,6 +105,22 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(uint32_t a)
     return __funnelshift_r(lds_u32(al), lds_u32(al + 4), a * 8);      // the funnel shift wraps at 32: (a * 8) & 31 = (a & 3) * 8
 }
 
+// Lanes of the (full) warp holding the same NBITS-bit key, as a lane mask: one ballot per key bit, the masks of
+// the bits a lane agrees with ANDed together.  Same result as __match_any_sync for keys below 2^NBITS, but in
+// NBITS ballots -- MATCH.ANY takes ~1700 cycles on 32 distinct keys here (it was three quarters of the chain
+// build, measured with clock64), the ballots a tenth of that.
+template <int NBITS>
+__device__ __forceinline__ uint32_t match_any_bits(uint32_t key)
+{
+    uint32_t grp = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b < NBITS; b++) {
+        const uint32_t vote = __ballot_sync(0xFFFFFFFFu, (key >> b) & 1u);
+        grp &= ((key >> b) & 1u) ? vote : ~vote;
+    }
+    return grp;
+}
+
 // length of the common prefix of x[a..] and x[b..], at most cap.  Both streams are read as ALIGNED words with
 // the previous word carried in a register (one load + one funnel shift per stream per 4 bytes, two steps per
 // trip); reads up to 11 bytes past the last compared byte, inside the look-ahead padding of xs.
@@ -133,21 +153,22 @@ struct MatchCtx {
     int minSlot;
 };
 
-__device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, int &bestLOut, int &bestSOut)
+// Candidates are the chain entries with slot in [lo, hi): the whole window [max(si - 2047, block start), si) for a
+// position evaluated by one lane, a part of it when several lanes share a position (lazy tiles).
+__device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, int lo, int hi, int &bestLOut, int &bestSOut)
 {
     const uint32_t xsB = c.xsB, upB = c.upB;
     int bestL = kMinLen - 1, bestS = 0;
     const uint32_t xi = xsB + si;
     const uint32_t wsi0 = lds_u32_unaligned(xi), wsi1 = lds_u32_unaligned(xi + 4);
     const uint32_t h = hash24(wsi0, MT_HBITS);
-    const int lo = max(si - kWindow, c.minSlot);
     const int sr0 = lo >> 10;
     uint32_t mLo = 0x00FFFFFFu, mHi = 0u;               // bytes 0..bestL must agree to beat bestL
     // one ascending chain per bucket over the whole region: enter it at the first sub-region the window touches
     int s = (int)lds_u16(c.headB + 2 * (sr0 * MT_HB + h));
     while (s < lo) s = (int)lds_u16(upB + 2 * s);       // entries before the window (MT_NONE = 0xFFFF ends it)
     for (;;) {
-        if (s >= si) break;                             // chain exhausted (MT_NONE >= si as well)
+        if (s >= hi) break;                             // range exhausted (MT_NONE >= hi as well)
         const int cur = s;
         s = (int)lds_u16(upB + 2 * cur);
         const uint32_t a = xsB + cur, al = a & ~3u, sh = a * 8;    // wrapping funnel shift: (a & 3) * 8
@@ -207,7 +228,9 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
             const int half = msb > 0 ? (int)((est >> (msb - 1)) & 1u) : 0;
             return (uint32_t)min(MT_BINS - 1, 1 + 2 * msb + half);
         };
-        // a thread bins the same 16 positions in both passes: keep the bins in registers (8 bits each)
+        // a thread bins the same 16 positions in both passes: keep the bins in registers (8 bits each).  Plain
+        // shared-memory atomics, one per position: lanes that hit the same bin are serialised by the hardware, which
+        // is still far cheaper than grouping them first (MATCH.ANY, or six ballots per position and their live ranges)
         uint32_t binPack[MT_PER_THREAD / 4];
 #pragma unroll
         for (int k = 0; k < MT_PER_THREAD; k++) {
@@ -215,8 +238,7 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
             const uint32_t bn = idx < tileSlots ? pos_bin(idx) : 0xFFu;
             if ((k & 3) == 0) binPack[k >> 2] = 0;
             binPack[k >> 2] |= bn << (8 * (k & 3));
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
-            if (bn != 0xFF && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&sm.binCount[bn], (uint32_t)__popc(grp));
+            if (bn != 0xFF) atomicAdd(&sm.binCount[bn], 1u);
         }
         __syncthreads();
         if (tid == 0) {                                    // heaviest bin first
@@ -228,12 +250,7 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
         for (int k = 0; k < MT_PER_THREAD; k++) {
             const int idx = k * MT_THREADS + tid;
             const uint32_t bn = (binPack[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
-            const int leader = __ffs(grp) - 1;
-            uint32_t base = 0;
-            if (bn != 0xFF && lane == leader) base = atomicAdd(&sm.binStart[bn], (uint32_t)__popc(grp));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (bn != 0xFF) sm.order[base + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)idx;
+            if (bn != 0xFF) sm.order[atomicAdd(&sm.binStart[bn], 1u)] = (uint16_t)idx;
         }
         __syncthreads();
     }
@@ -246,7 +263,7 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
         const int i = regionBase + si;
         const int cap = min(kMaxLen, n - 1 - i);
         int bestL = 0, bestS = 0;
-        if (i > 0 && cap >= kMinLen) match_one(ctx, si, cap, bestL, bestS);
+        if (i > 0 && cap >= kMinLen) match_one(ctx, si, cap, max(si - kWindow, minSlot), si, bestL, bestS);
         const bool hit = bestL >= kMinLen;
         lenCode[outBase + i] = hit ? (uint8_t)(bestL - 2) : (uint8_t)0;
         dist[outBase + i] = hit ? (uint16_t)(si - bestS) : (uint16_t)0;
@@ -280,21 +297,44 @@ __device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &c
     for (;;) {
         const uint32_t count = sm.binCount[0];
         if (count == 0) break;
-        for (uint32_t j = tid; j < count; j += MT_THREADS) {
-            const int p = cur[j];
-            if (p >= tileSlots) continue;
-            const uint32_t bit = 1u << (p & 31);
-            if (atomicOr(&bits[p >> 5], bit) & bit) continue;                // someone else owns this position
+        // A round with few positions gives each of them several lanes, every lane walking its share of the window:
+        // the late rounds follow a handful of chains that have not merged yet, one position each, ~50 candidates
+        // with long extensions per position, so what the tile waits for there is the latency of ONE evaluation (and a
+        // warp instruction costs the same with one lane as with 32).  Full rounds keep one lane per position: the
+        // shares cannot prune each other, which costs extensions.  Results are merged with the rule itself:
+        // longest, then farthest.
+        const int shift = count > MT_THREADS / 2 ? 0 : count > MT_THREADS / 4 ? 1 : count > MT_THREADS / 8 ? 2 : MT_LAZY_SPLIT_LOG2;
+        const int split = 1 << shift;
+        for (uint32_t base = 0; base < count; base += (uint32_t)(MT_THREADS >> shift)) {   // CTA-uniform trip count (shuffles inside)
+            const uint32_t g = base + (uint32_t)(tid >> shift);
+            const int part = tid & (split - 1);
+            const int p = g < count ? (int)cur[g] : tileSlots;
+            uint32_t mine = 0;
+            if (p < tileSlots && part == 0) {
+                const uint32_t bit = 1u << (p & 31);
+                mine = (atomicOr(&bits[p >> 5], bit) & bit) ? 0u : 1u;       // else someone else owns this position
+            }
+            mine = __shfl_sync(0xFFFFFFFFu, mine, (tid & 31) & ~(split - 1));
             const int si = MT_HALO + p;
             const int i = regionBase + si;
             const int cap = min(kMaxLen, n - 1 - i);
             int bestL = 0, bestS = 0;
-            if (i > 0 && cap >= kMinLen) match_one(ctx, si, cap, bestL, bestS);
-            const bool hit = bestL >= kMinLen;
-            lenCode[outBase + i] = hit ? (uint8_t)(bestL - 2) : (uint8_t)0;
-            dist[outBase + i] = hit ? (uint16_t)(si - bestS) : (uint16_t)0;
-            const int nx = p + (hit ? bestL : 0) + 1;                        // next parse cursor if p is one
-            if (nx < tileSlots && !((bits[nx >> 5] >> (nx & 31)) & 1u)) nxt[atomicAdd(&sm.binCount[1], 1u)] = (uint16_t)nx;
+            if (mine && i > 0 && cap >= kMinLen) {
+                const int lo = max(si - kWindow, ctx.minSlot);
+                const int q = (si - lo + split - 1) >> shift;
+                const int rlo = lo + part * q, rhi = min(si, rlo + q);
+                if (rlo < rhi) match_one(ctx, si, cap, rlo, rhi, bestL, bestS);
+            }
+            uint32_t key = bestL >= kMinLen ? ((uint32_t)bestL << 13) | (0x1FFFu - (uint32_t)bestS) : 0u;
+            for (int d = 1; d < split; d <<= 1) key = max(key, __shfl_xor_sync(0xFFFFFFFFu, key, d));
+            if (mine && part == 0) {
+                const bool hit = key != 0u;
+                const int L = (int)(key >> 13), S = 0x1FFF - (int)(key & 0x1FFFu);
+                lenCode[outBase + i] = hit ? (uint8_t)(L - 2) : (uint8_t)0;
+                dist[outBase + i] = hit ? (uint16_t)(si - S) : (uint16_t)0;
+                const int nx = p + (hit ? L : 0) + 1;                        // next parse cursor if p is one
+                if (nx < tileSlots && !((bits[nx >> 5] >> (nx & 31)) & 1u)) nxt[atomicAdd(&sm.binCount[1], 1u)] = (uint16_t)nx;
+            }
         }
         __syncthreads();
         if (tid == 0) { sm.binCount[0] = sm.binCount[1]; sm.binCount[1] = 0; }
@@ -303,7 +343,7 @@ __device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &c
     }
 }
 
-__global__ void __launch_bounds__(MT_THREADS)
+__global__ void __launch_bounds__(MT_THREADS, 5)
 k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist, int forceEager)
 {
@@ -353,8 +393,10 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const int pos = regionBase + slot;
             const bool valid = pos >= 0 && pos + 3 <= n;
             const uint32_t h = hash24(ld32u(sm.xs, slot), MT_HBITS);
-            const uint32_t key = valid ? h : (0x80000000u | lane);
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
+            // invalid lanes (outside the block) match nobody: the valid ballot separates them, then each stands alone
+            const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+            const uint32_t same = match_any_bits<MT_HBITS>(h);            // every lane votes, valid or not
+            const uint32_t grp = valid ? (same & vmask) : (1u << lane);
             const uint32_t higher = (lane == 31) ? 0u : (grp & ~((2u << lane) - 1u));
             uint32_t old = MT_NONE, oldPop = 0;
             if (valid) { old = head[h]; oldPop = pop[h >> 1]; }
@@ -415,7 +457,7 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
                 // the probe only has to tell "mean length >= 12" from "short": matches are followed to 40 bytes at
                 // most (one probe lane walking a 257-byte match kept the other 192 threads at the barrier)
                 int bl = 0, bs = 0;
-                match_one(ctx, si, min(cap, MT_PROBE_CAP), bl, bs);
+                match_one(ctx, si, min(cap, MT_PROBE_CAP), max(si - kWindow, minSlot), si, bl, bs);
                 L = bl >= kMinLen ? bl : 0;
             }
         }
