@@ -9,7 +9,7 @@
 // One CTA owns a tile of 4096 positions and stages tile + 2048 bytes of history + 272 bytes
 // of look-ahead in shared memory.  The 6144-slot region is cut into six 1024-slot
 // sub-regions; warp w threads the positions of sub-region w into ASCENDING per-hash chains
-// (hash of the 3-byte gram) with a ballot-built lane mask per hash value, walking its chunks from the top so that
+// (hash of the 3-byte gram) with __match_any_sync, walking its chunks from the top so that
 // head[] ends up holding the lowest slot and up[] the next higher slot of the same hash;
 // head[] also carries the bucket population.
 // The six chains of a bucket are then linked into one ascending chain over the whole region
@@ -103,22 +103,6 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(uint32_t a)
 {
     const uint32_t al = a & ~3u;
     return __funnelshift_r(lds_u32(al), lds_u32(al + 4), a * 8);      // the funnel shift wraps at 32: (a * 8) & 31 = (a & 3) * 8
-}
-
-// Lanes of the (full) warp holding the same NBITS-bit key, as a lane mask: one ballot per key bit, the masks of
-// the bits a lane agrees with ANDed together.  Same result as __match_any_sync for keys below 2^NBITS, but in
-// NBITS ballots -- MATCH.ANY takes ~1700 cycles on 32 distinct keys here (it was three quarters of the chain
-// build, measured with clock64), the ballots a tenth of that.
-template <int NBITS>
-__device__ __forceinline__ uint32_t match_any_bits(uint32_t key)
-{
-    uint32_t grp = 0xFFFFFFFFu;
-#pragma unroll
-    for (int b = 0; b < NBITS; b++) {
-        const uint32_t vote = __ballot_sync(0xFFFFFFFFu, (key >> b) & 1u);
-        grp &= ((key >> b) & 1u) ? vote : ~vote;
-    }
-    return grp;
 }
 
 // length of the common prefix of x[a..] and x[b..], at most cap.  Both streams are read as ALIGNED words with
@@ -228,9 +212,7 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
             const int half = msb > 0 ? (int)((est >> (msb - 1)) & 1u) : 0;
             return (uint32_t)min(MT_BINS - 1, 1 + 2 * msb + half);
         };
-        // a thread bins the same 16 positions in both passes: keep the bins in registers (8 bits each).  Plain
-        // shared-memory atomics, one per position: lanes that hit the same bin are serialised by the hardware, which
-        // is still far cheaper than grouping them first (MATCH.ANY, or six ballots per position and their live ranges)
+        // a thread bins the same 16 positions in both passes: keep the bins in registers (8 bits each)
         uint32_t binPack[MT_PER_THREAD / 4];
 #pragma unroll
         for (int k = 0; k < MT_PER_THREAD; k++) {
@@ -238,7 +220,8 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
             const uint32_t bn = idx < tileSlots ? pos_bin(idx) : 0xFFu;
             if ((k & 3) == 0) binPack[k >> 2] = 0;
             binPack[k >> 2] |= bn << (8 * (k & 3));
-            if (bn != 0xFF) atomicAdd(&sm.binCount[bn], 1u);
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
+            if (bn != 0xFF && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&sm.binCount[bn], (uint32_t)__popc(grp));
         }
         __syncthreads();
         if (tid == 0) {                                    // heaviest bin first
@@ -250,7 +233,12 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
         for (int k = 0; k < MT_PER_THREAD; k++) {
             const int idx = k * MT_THREADS + tid;
             const uint32_t bn = (binPack[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            if (bn != 0xFF) sm.order[atomicAdd(&sm.binStart[bn], 1u)] = (uint16_t)idx;
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, bn);
+            const int leader = __ffs(grp) - 1;
+            uint32_t base = 0;
+            if (bn != 0xFF && lane == leader) base = atomicAdd(&sm.binStart[bn], (uint32_t)__popc(grp));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (bn != 0xFF) sm.order[base + __popc(grp & ((1u << lane) - 1u))] = (uint16_t)idx;
         }
         __syncthreads();
     }
@@ -343,7 +331,7 @@ __device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &c
     }
 }
 
-__global__ void __launch_bounds__(MT_THREADS, 5)
+__global__ void __launch_bounds__(MT_THREADS)
 k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist, int forceEager)
 {
@@ -393,10 +381,8 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const int pos = regionBase + slot;
             const bool valid = pos >= 0 && pos + 3 <= n;
             const uint32_t h = hash24(ld32u(sm.xs, slot), MT_HBITS);
-            // invalid lanes (outside the block) match nobody: the valid ballot separates them, then each stands alone
-            const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-            const uint32_t same = match_any_bits<MT_HBITS>(h);            // every lane votes, valid or not
-            const uint32_t grp = valid ? (same & vmask) : (1u << lane);
+            const uint32_t key = valid ? h : (0x80000000u | lane);
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
             const uint32_t higher = (lane == 31) ? 0u : (grp & ~((2u << lane) - 1u));
             uint32_t old = MT_NONE, oldPop = 0;
             if (valid) { old = head[h]; oldPop = pop[h >> 1]; }
