@@ -147,7 +147,6 @@ struct EmitSmem {
     uint32_t pbits[368];
     uint32_t gbits[128];
     unsigned long long base;              // look-back result: packed exclusive ranks of the tile's first token
-    uint16_t exitOf[PT_ENTRIES + 6];      // the tile's exit function (only consulted when it is not constant)
     uint32_t exit0, entry;
 };
 
@@ -350,27 +349,35 @@ k_parse(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
     for (int k = tid; k < 128; k += PT_THREADS) sm.gbits[k] = 0;
     const bool plain = build_jumps(sm.j, lenCode + (size_t)b * kBlockBytes, tb, limit);
 
-    // ---- exit function: where does a chain entering at offset e leave?  <= 16 hops, one mid-tile each ----
+    // ---- exit function: where does a chain entering at offset e leave?  All 258 chains advance one mid-tile per
+    // round (one J2 hop) until they stand on the same position -- they merge after a token or two, so that is
+    // round 1 or 2 -- and from there ONE thread follows the common chain to the end of the tile.  If they never
+    // meet the exit depends on the entry.
     {
-        int e = tid;
-        while (e < PT) e = sm.j.J2[jphys(e)];
-        sm.exitOf[tid] = (uint16_t)(e - PT);
-        if (tid == 0) sm.exit0 = (uint32_t)(e - PT);
-        bool same = true;
-        if (tid < PT_ENTRIES - PT_THREADS) {                   // entries 256, 257
-            int e2 = PT_THREADS + tid;
-            while (e2 < PT) e2 = sm.j.J2[jphys(e2)];
-            sm.exitOf[PT_THREADS + tid] = (uint16_t)(e2 - PT);
-            same = e2 == e;                                    // compared with the first entry below through e
+        int e = tid, e2 = PT_THREADS + tid;                    // entries 0..255; threads 0, 1 also carry entries 256, 257
+        bool constant = false;
+        for (int lvl = 1; lvl <= PT / 256; lvl++) {
+            const int bound = lvl * 256;
+            if (e < bound) e = sm.j.J2[jphys(e)];              // leaves mid-tile lvl - 1 (a long match may already be beyond)
+            if (tid < PT_ENTRIES - PT_THREADS && e2 < bound) e2 = sm.j.J2[jphys(e2)];
+            if (tid == 0) sm.exit0 = (uint32_t)e;
+            __syncthreads();
+            const bool same = e == (int)sm.exit0 && (tid >= PT_ENTRIES - PT_THREADS || e2 == (int)sm.exit0);
+            if (__syncthreads_and(same)) { constant = true; break; }
         }
-        __syncthreads();
-        same = same && (uint32_t)(e - PT) == sm.exit0;
-        const bool constant = __syncthreads_and(same) != 0;
-        // entry: the exit of the tile before this one.  A constant tile has told its successor already.
+        // entry: the exit of the tile before this one.  A constant tile tells its successor before it knows its own.
         if (tid == 0) {
-            if (constant) exit_publish(exitRow, tile, sm.exit0);
+            if (constant) {
+                int ex = e;
+                while (ex < PT) ex = sm.j.J2[jphys(ex)];
+                exit_publish(exitRow, tile, (uint32_t)(ex - PT));
+            }
             const uint32_t en = tile ? exit_wait(exitRow, tile - 1) : 0u;
-            if (!constant) exit_publish(exitRow, tile, sm.exitOf[en]);
+            if (!constant) {
+                int ex = (int)en;
+                while (ex < PT) ex = sm.j.J2[jphys(ex)];
+                exit_publish(exitRow, tile, (uint32_t)(ex - PT));
+            }
             sm.entry = en;
         }
         __syncthreads();
