@@ -366,7 +366,9 @@ static int decompress_device(fcx_ctx *c, const uint8_t *d_file, const uint64_t *
         const uint32_t nb = std::min(kBatch, nBlocks - b0);
         // pageable source: the copy returns once the offsets are staged, so the caller's array may change afterwards
         CK(cudaMemcpyAsync(c->decRec, recOff + b0, sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, st));
-        c->launches += launch_decode(d_file, c->decRec, nb, d_out + (size_t)b0 * kBlockBytes, c->decLen, c->decScratch, per, st, x9);
+        const int nl = launch_decode(d_file, c->decRec, nb, d_out + (size_t)b0 * kBlockBytes, c->decLen, c->decScratch, per, st, x9);
+        if (nl < 0) return fail(FCX_ERR_CUDA, "decode kernels failed to launch");
+        c->launches += nl;
         CK(cudaMemcpyAsync(lens + b0, c->decLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));

@@ -5,7 +5,10 @@
 
 namespace fcx {
 
-constexpr int DEC_THREADS = 256;
+#ifndef FCX_DEC_THREADS
+#define FCX_DEC_THREADS 512
+#endif
+constexpr int DEC_THREADS = FCX_DEC_THREADS;   // lanes of a decoder CTA (256 or 512)
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int DEC_LUT_BITS = 11;
 constexpr int DEC_LUT = 1 << DEC_LUT_BITS;
@@ -18,7 +21,7 @@ __device__ __forceinline__ uint32_t rd32(const uint8_t *p)
 }
 
 // =========================================================================================
-// speculative parallel decode of one prefix-coded stream by a 256-lane CTA
+// speculative parallel decode of one prefix-coded stream by one CTA (DEC_THREADS lanes)
 // =========================================================================================
 // ---- per-lane bit cursor over little-endian 32-bit words at any byte address -------------------
 template <bool kConst>

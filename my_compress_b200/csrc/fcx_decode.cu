@@ -168,9 +168,9 @@ k_dec_sections(const uint8_t *__restrict__ file, const uint64_t *__restrict__ re
 // =========================================================================================
 // 3: match lengths, then the byte-parallel token replay
 // =========================================================================================
-constexpr uint32_t RP_RING = 16384;                 // >= 2047 (window) + RP_BYTES (one batch)
+constexpr uint32_t RP_RING = DEC_THREADS <= 256 ? 16384 : 32768;   // power of two >= 2047 (window) + RP_BYTES (one batch) + 258
 constexpr uint32_t RP_MASK = RP_RING - 1;
-constexpr uint32_t RP_BYTES = 8192;                 // output bytes per batch at most
+constexpr uint32_t RP_BYTES = DEC_THREADS <= 512 ? 32u * DEC_THREADS : 16384u;     // output bytes per batch at most (batch-relative positions are 16-bit)
 constexpr int RP_PER = 8;                           // tokens a thread gathers: one flag byte
 constexpr uint32_t RP_TOKENS = DEC_THREADS * RP_PER;      // 2048
 constexpr uint32_t RP_NONE = 0xFFFD, RP_STOP = 0xFFFE, RP_BADTOK = 0xFFFF;
@@ -391,12 +391,15 @@ void decode_init()
 int launch_decode(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t nBlocks, uint8_t *d_out,
                   uint32_t *d_outLen, uint8_t *d_scratch, size_t scratchPerBlock, cudaStream_t st, bool x9)
 {
+    // k_dec_replay needs more than 48 KB of dynamic shared memory: opt in on whatever device is current (a process
+    // that only ever decodes never creates a compress context, which is where the other kernels are set up)
+    decode_init();
     // the reference decodes into zero-initialised buffers (mc:2270,2282,2291,2305)
     cudaMemsetAsync(d_scratch, 0, scratchPerBlock * nBlocks, st);
     k_dec_parse<<<(nBlocks + 127) / 128, 128, 0, st>>>(d_file, d_recOff, nBlocks, d_scratch, scratchPerBlock, x9);
     k_dec_sections<<<dim3(4, nBlocks), DEC_THREADS, 0, st>>>(d_file, d_recOff, d_scratch, scratchPerBlock);
     k_dec_replay<<<nBlocks, DEC_THREADS, sizeof(ReplaySmem), st>>>(d_out, d_outLen, d_scratch, scratchPerBlock);
-    return 3;
+    return cudaGetLastError() == cudaSuccess ? 3 : -1;          // a kernel that did not launch must not read as "decoded 0 bytes"
 }
 
 } // namespace fcx

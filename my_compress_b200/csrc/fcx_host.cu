@@ -496,8 +496,11 @@ int decompress_host(const uint8_t *file, const std::vector<uint64_t> &rec, uint6
             }
             const GBatch &b = batches[my[k]];
             cuda_ok(cudaStreamWaitEvent(s.stream, s.evIn[k], 0), "wait");
-            launch_decode(s.dIn, s.decRec + blk0[k], b.nBlocks, s.dOut + (uint64_t)(k % kDecRing) * maxBatch * kBlockBytes,
-                          s.decLen + blk0[k], s.decScratch, per, s.stream, x9);
+            if (launch_decode(s.dIn, s.decRec + blk0[k], b.nBlocks, s.dOut + (uint64_t)(k % kDecRing) * maxBatch * kBlockBytes,
+                              s.decLen + blk0[k], s.decScratch, per, s.stream, x9) < 0) {
+                rc = fail(FCX_ERR_CUDA, "decode kernels failed to launch");
+                break;
+            }
             cuda_ok(cudaMemcpyAsync(s.hostLen + blk0[k], s.decLen + blk0[k], sizeof(uint32_t) * b.nBlocks, cudaMemcpyDeviceToHost, s.stream), "D2H");
             cuda_ok(cudaEventRecord(s.evOut[k], s.stream), "event");
         }
@@ -693,7 +696,8 @@ int decompress_lz78_host(const uint8_t *file, const std::vector<uint64_t> &rec, 
         for (uint32_t i = 0; i < nb; i++) offs[i] = rec[b0 + i] - f0;
         if (cudaMemcpyAsync(dRec, offs, sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
             return done(fail(FCX_ERR_CUDA, "H2D copy failed"));
-        launch_decode_lz78(s.dIn, dRec, nb, s.dOut, kStride, dLen, s.decScratch, per, s.stream);
+        if (launch_decode_lz78(s.dIn, dRec, nb, s.dOut, kStride, dLen, s.decScratch, per, s.stream) < 0)
+            return done(fail(FCX_ERR_CUDA, "lz78 decode kernel failed to launch"));
         if (cudaMemcpyAsync(lens, dLen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
             cudaStreamSynchronize(s.stream) != cudaSuccess)
             return done(fail(FCX_ERR_CUDA, std::string("lz78 decode: ") + cudaGetErrorString(cudaGetLastError())));

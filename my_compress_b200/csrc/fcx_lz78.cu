@@ -759,7 +759,7 @@ int launch_decode_lz78(const uint8_t *d_file, const uint64_t *d_recOff, uint32_t
     cudaMemsetAsync(d_scratch, 0, scratchPerBlock * nBlocks, st);
     k78_decode<<<nBlocks, DEC_THREADS, sizeof(D8Smem), st>>>(d_file, d_recOff, d_out, d_outLen, d_scratch, scratchPerBlock,
                                                                 outStride, (uint32_t)std::min<size_t>(outStride, kBlockBytes + 8));
-    return 1;
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 } // namespace fcx
