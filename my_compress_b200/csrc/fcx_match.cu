@@ -381,11 +381,21 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const int pos = regionBase + slot;
             const bool valid = pos >= 0 && pos + 3 <= n;
             const uint32_t h = hash24(ld32u(sm.xs, slot), MT_HBITS);
-            const uint32_t key = valid ? h : (0x80000000u | lane);
-            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
-            const uint32_t higher = (lane == 31) ? 0u : (grp & ~((2u << lane) - 1u));
+            // Lanes of this step that share a hash value must be threaded in slot order, which needs the groups
+            // (MATCH.ANY) -- a slow instruction: a clock64 trace put a step at ~1700 cycles, and hashing several steps
+            // ahead so that their MATCH.ANYs overlap made the kernel slower, i.e. they queue on one unit.  On
+            // incompressible input most steps have no two lanes in one bucket: every lane stores its slot in head[h] and
+            // reads it back; if everybody reads its own slot there was no collision and each lane is its own group
+            // (uniform-256MiB: 3.48 -> 3.24 ms).  head[h] is rewritten properly below either way; `old` is read first.
             uint32_t old = MT_NONE, oldPop = 0;
             if (valid) { old = head[h]; oldPop = pop[h >> 1]; }
+            __syncwarp();
+            if (valid) head[h] = (uint16_t)slot;
+            __syncwarp();
+            const bool lost = valid && head[h] != (uint16_t)slot;
+            uint32_t grp = 1u << lane;
+            if (__any_sync(0xFFFFFFFFu, lost)) grp = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x80000000u | lane));   // (grouping only the colliding lanes: same speed)
+            const uint32_t higher = (lane == 31) ? 0u : (grp & ~((2u << lane) - 1u));
             __syncwarp();
             if (valid) {
                 sm.up[slot] = higher ? (uint16_t)(sr * MT_SUB + ch * 32 + (__ffs(higher) - 1)) : (uint16_t)old;
