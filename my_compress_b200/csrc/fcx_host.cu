@@ -102,6 +102,22 @@ std::vector<uint32_t> pipeline_plan(uint64_t blocks)
     std::vector<uint32_t> plan;
     if (blocks <= FCX_PIPE_MIN_BLOCKS) { if (blocks) plan.push_back((uint32_t)blocks); return plan; }
     const uint64_t B = blocks;
+    if (B >= 512) {
+        // large inputs: batches double from 8 blocks to 256 (the upload of batch k+1 then fits behind the kernels of
+        // batch k from the start: the kernels take ~1.5x as long per MiB as the copy), 256-block batches in the middle,
+        // and a tail that shrinks by 2.5x per batch down to 8 so that every download hides behind the next batch's
+        // kernels.  Measured on mixed-1GiB against the plan below: 33.96 -> 33.31 ms per call.
+        std::vector<uint32_t> up, down;
+        uint64_t used = 0;
+        for (uint64_t s = 8; s < 256 && used + s <= B / 2; s = s * 5 / 2) { down.push_back((uint32_t)s); used += s; }
+        for (uint64_t s = 8; s < 256 && used + s <= B; s *= 2) { up.push_back((uint32_t)s); used += s; }
+        // never more batches than the per-device event pool holds: the middle ones grow instead (<= kMaxBatchBlocks each)
+        const uint64_t rem = B - used, k = std::min<uint64_t>((rem + 255) / 256, kMaxPipeBatches - 16);
+        for (uint32_t s : up) plan.push_back(s);
+        for (uint64_t i = 0; i < k; i++) plan.push_back((uint32_t)(rem * (i + 1) / k - rem * i / k));
+        for (size_t i = down.size(); i-- > 0;) plan.push_back(down[i]);
+        return plan;
+    }
     const uint32_t edge = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(2, B / 16));
     uint64_t rem = B - 2 * edge;
     plan.push_back(edge);

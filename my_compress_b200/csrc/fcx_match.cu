@@ -291,10 +291,14 @@ __device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &c
         // warp instruction costs the same with one lane as with 32).  Full rounds keep one lane per position: the
         // shares cannot prune each other, which costs extensions.  Results are merged with the rule itself:
         // longest, then farthest.
-        const int shift = count > MT_THREADS / 2 ? 0 : count > MT_THREADS / 4 ? 1 : count > MT_THREADS / 8 ? 2 : MT_LAZY_SPLIT_LOG2;
-        const int split = 1 << shift;
-        for (uint32_t base = 0; base < count; base += (uint32_t)(MT_THREADS >> shift)) {   // CTA-uniform trip count (shuffles inside)
+        // (the lanes per position are chosen per trip from what is left of the round: 377 positions run as 256 with
+        // one lane each, then 121 with two)
+        for (uint32_t base = 0; base < count;) {                                          // CTA-uniform trips (shuffles inside)
+            const uint32_t left = count - base;
+            const int shift = left > MT_THREADS / 2 ? 0 : left > MT_THREADS / 4 ? 1 : left > MT_THREADS / 8 ? 2 : MT_LAZY_SPLIT_LOG2;
+            const int split = 1 << shift;
             const uint32_t g = base + (uint32_t)(tid >> shift);
+            base += (uint32_t)(MT_THREADS >> shift);
             const int part = tid & (split - 1);
             const int p = g < count ? (int)cur[g] : tileSlots;
             uint32_t mine = 0;
