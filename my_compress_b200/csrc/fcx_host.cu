@@ -662,7 +662,7 @@ int compress_lz78_host(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out
     const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
     // lz78 payloads can exceed the lz77 bound (32-bit tree nodes, group codes): the reference's own buffer is 2 MiB per block
     const uint64_t bound = 10 + nBlocks * (4 + (5ull << 19) + (1ull << 20) + 4096) + 64;
-    int rc = slot_prepare_compress(s, devs[0], std::max<uint64_t>(n, 16), bound, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nBlocks, 1), 256));
+    int rc = slot_prepare_compress(s, devs[0], std::max<uint64_t>(n, 16), bound, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nBlocks, 1), kMaxBatchBlocks));
     if (rc) return rc;
     if (n) CK(cudaMemcpyAsync(s.dIn, in, n, cudaMemcpyHostToDevice, s.stream));
     uint64_t got = 0;

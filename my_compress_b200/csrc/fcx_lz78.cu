@@ -62,34 +62,38 @@ k78_tokenize(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen
     uint8_t *c = cArena + (size_t)b * cStride;
     uint32_t root[256];                                  // children of the empty phrase (local memory, L1-resident)
     for (int k = 0; k < 256; k++) root[k] = 0;
-    uint32_t T = 0, next = 1, cur = 0;
+    // A flat step loop: every trip a lane does ONE dictionary probe (the dependent HBM access) or emits a one-byte
+    // phrase.  With the descent as an inner loop the lanes of a warp -- 32 different blocks -- waited for the longest
+    // phrase among them before any of them could start its next token (a block of random bytes, 2.5 bytes per phrase,
+    // moved at the pace of a neighbour with 30-byte phrases).
+    uint32_t T = 0, next = 1, cur = 0, k = 0, node = 0;       // phrase start, bytes of it matched so far, its dictionary node
     while (cur < n) {
-        const uint32_t b0 = x[cur];
-        uint32_t node = root[b0];
-        if (node == 0) {                                 // a new one-byte phrase
-            root[b0] = next++;                           // mc:1878: ++dictIdx after every emitted token
-            idx[T] = 0; c[T] = (uint8_t)b0; T++;
-            cur += 1;
-            continue;
+        if (k == 0) {
+            const uint32_t b0 = x[cur];
+            node = root[b0];
+            if (node == 0) {                             // a new one-byte phrase
+                root[b0] = next++;                       // mc:1878: ++dictIdx after every emitted token
+                idx[T] = 0; c[T] = (uint8_t)b0; T++;
+                cur += 1;
+                continue;
+            }
+            k = 1;
         }
-        uint32_t k = 1;
-        for (;;) {                                       // descend while phrase + next byte is known
-            if (cur + k >= n) {                          // ran out of input inside a known phrase (mc:1858-1862)
-                idx[T] = node; c[T] = 0; T++;
-                cur = n;
-                break;
-            }
-            const uint32_t by = x[cur + k];
-            const unsigned long long kk = (unsigned long long)((node << 8) | by) + 1;
-            uint32_t slot = l8_hash((uint32_t)kk);
-            unsigned long long e;
-            while ((e = tab[slot]) != 0 && (e >> 32) != kk) slot = (slot + 1) & (L8_TABLE_SLOTS - 1);
-            if (e == 0) {                                // phrase + this byte is new
-                tab[slot] = (kk << 32) | next++;
-                idx[T] = node; c[T] = (uint8_t)by; T++;
-                cur += k + 1;
-                break;
-            }
+        if (cur + k >= n) {                              // ran out of input inside a known phrase (mc:1858-1862)
+            idx[T] = node; c[T] = 0; T++;
+            break;
+        }
+        const uint32_t by = x[cur + k];
+        const unsigned long long kk = (unsigned long long)((node << 8) | by) + 1;
+        uint32_t slot = l8_hash((uint32_t)kk);
+        unsigned long long e;
+        while ((e = tab[slot]) != 0 && (e >> 32) != kk) slot = (slot + 1) & (L8_TABLE_SLOTS - 1);
+        if (e == 0) {                                    // phrase + this byte is new
+            tab[slot] = (kk << 32) | next++;
+            idx[T] = node; c[T] = (uint8_t)by; T++;
+            cur += k + 1;
+            k = 0;
+        } else {                                         // known: descend
             node = (uint32_t)e;
             k++;
         }
@@ -441,7 +445,9 @@ int lz78_compress_device(fcx_ctx *c, const uint8_t *d_in, uint64_t n, uint8_t *d
                          uint64_t hdrBytes, uint32_t hdrBlocks, uint64_t *outBytes)
 {
     const uint64_t nBlocks = (n + kBlockBytes - 1) / kBlockBytes;
-    const uint32_t batch = std::min<uint32_t>(c->maxBlocks, 256);
+    // blocks in flight are the tokenizer's only parallelism (one thread per block, one dependent probe per byte):
+    // a batch is as large as the context allows -- 12.6 MiB of lz78 workspace per block, 13 GB for 1024 blocks
+    const uint32_t batch = std::min<uint32_t>(c->maxBlocks, kMaxBatchBlocks);
     std::string err;
     Lz78Host *h = lz78_get(c, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nBlocks, 1), batch), err);
     if (!h) return fail(FCX_ERR_CUDA, err);
