@@ -37,12 +37,16 @@
 namespace fcx {
 
 constexpr int MT_TILE = 4096;
-constexpr int MT_SUB = 1024;
+#ifndef FCX_MT_SUBBITS
+#define FCX_MT_SUBBITS 10           // slots per sub-region = buckets per sub-region = 2^this (10: six sub-regions, 11: three)
+#endif
+constexpr int MT_SUBBITS = FCX_MT_SUBBITS;
+constexpr int MT_SUB = 1 << MT_SUBBITS;
 constexpr int MT_HALO = 2048;
 constexpr int MT_REGION = MT_TILE + MT_HALO;     // 6144 slots
 constexpr int MT_NSUB = MT_REGION / MT_SUB;      // 6
 #ifndef FCX_MT_HBITS
-#define FCX_MT_HBITS 10          // 11 drops a resident CTA, 9 doubles collisions: both measured slower
+#define FCX_MT_HBITS FCX_MT_SUBBITS   // (six sub-regions with 11 bits drop a resident CTA, 9 bits double the collisions: both measured slower)
 #endif
 #ifndef FCX_MT_SPEC_STRIDE
 #define FCX_MT_SPEC_STRIDE 32    // 16/32/64/128 measured on the phrase corpus: 32 best
@@ -74,9 +78,9 @@ struct MatchSmem {
     uint32_t binStart[MT_BINS];
     uint32_t maxPop;
     uint32_t probeSum;
-    uint16_t tail4[MT_HB];                       // chain tails of sub-region 4 while the chains are linked (0..3: order[])
+    uint16_t tail4[(MT_NSUB - 1) * MT_HB > MT_TILE ? MT_HB : 2];                       // chain tails of sub-region 4 while the chains are linked (0..3: order[])
 };
-static_assert(MT_NSUB == 6 && MT_TILE == 4 * MT_HB, "chain tails of sub-regions 0..3 fit order[], sub-region 4 has tail4[], 5 needs none");
+static_assert((MT_NSUB - 1) * MT_HB <= MT_TILE + MT_HB && MT_NSUB * MT_SUB == MT_REGION, "chain tails of all sub-regions but the last fit order[] + tail4[] (the last needs none)");
 
 // ---- explicit shared-memory loads (32-bit shared addresses held in registers) -------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -146,7 +150,7 @@ __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, in
     const uint32_t xi = xsB + si;
     const uint32_t wsi0 = lds_u32_unaligned(xi), wsi1 = lds_u32_unaligned(xi + 4);
     const uint32_t h = hash24(wsi0, MT_HBITS);
-    const int sr0 = lo >> 10;
+    const int sr0 = lo >> MT_SUBBITS;
     uint32_t mLo = 0x00FFFFFFu, mHi = 0u;               // bytes 0..bestL must agree to beat bestL
     // one ascending chain per bucket over the whole region: enter it at the first sub-region the window touches
     int s = (int)lds_u16(c.headB + 2 * (sr0 * MT_HB + h));
@@ -206,7 +210,7 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
             const uint32_t h = hash24(lds_u32_unaligned(xsA + si), MT_HBITS);
             const int lo = max(si - kWindow, minSlot);
             uint32_t est = 0;
-            for (int sr = lo >> 10; sr <= (si >> 10); sr++) est += lds_u8(ctx.popB + sr * (MT_HB / 2) + (h >> 1));
+            for (int sr = lo >> MT_SUBBITS; sr <= (si >> MT_SUBBITS); sr++) est += lds_u8(ctx.popB + sr * (MT_HB / 2) + (h >> 1));
             if (!est) return 0u;
             const int msb = 31 - __clz(est);
             const int half = msb > 0 ? (int)((est >> (msb - 1)) & 1u) : 0;
@@ -378,7 +382,7 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         const int sr = warp;
         uint16_t *head = sm.head + sr * MT_HB;
         uint8_t *pop = sm.pop + sr * (MT_HB / 2);
-        uint16_t *tail = sr < 4 ? sm.order + sr * MT_HB : sm.tail4;   // highest slot of every bucket of this sub-region (not kept for the last one)
+        uint16_t *tail = (sr + 1) * MT_HB <= MT_TILE ? sm.order + sr * MT_HB : sm.tail4;   // highest slot of every bucket of this sub-region (not kept for the last one)
         uint32_t myMax = 0;
         for (int ch = MT_SUB / 32 - 1; ch >= 0; ch--) {
             const int slot = sr * MT_SUB + ch * 32 + lane;
@@ -424,7 +428,7 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
         for (int sr = MT_NSUB - 2; sr >= 0; sr--) {
             const uint32_t hd = sm.head[sr * MT_HB + h];
             if (hd != MT_NONE) {
-                const uint32_t t = sr < 4 ? sm.order[sr * MT_HB + h] : sm.tail4[h];
+                const uint32_t t = (sr + 1) * MT_HB <= MT_TILE ? sm.order[sr * MT_HB + h] : sm.tail4[h];
                 sm.up[t] = (uint16_t)nextHead;
                 nextHead = hd;
             } else
