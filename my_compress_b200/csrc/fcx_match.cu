@@ -65,6 +65,7 @@ constexpr int MT_LONG_MEAN = 12;                      // mean probed match lengt
 constexpr int MT_LAZY_SPLIT_LOG2 = FCX_MT_LAZY_SPLIT_LOG2;            // lazy mode: up to 2^this lanes per position in rounds with few positions
 constexpr int MT_SPEC_STRIDE = FCX_MT_SPEC_STRIDE;                    // lazy mode: a speculative chain starts every 32 positions
 constexpr uint32_t MT_NONE = 0xFFFF;
+constexpr int MT_DENSE_TRIPS = 15;                // after 64 skipped entries the window's first slots are tried directly
 constexpr int MT_BINS = 32;
 constexpr uint32_t MT_SORT_THRESHOLD = 12;       // sort only when some bucket holds more than this
 
@@ -143,6 +144,8 @@ struct MatchCtx {
 
 // Candidates are the chain entries with slot in [lo, hi): the whole window [max(si - 2047, block start), si) for a
 // position evaluated by one lane, a part of it when several lanes share a position (lazy tiles).
+// DENSE (lazy tiles only: that is where runs end up): the shortcut for buckets that hold most slots, see below.
+template <bool DENSE = false>
 __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, int lo, int hi, int &bestLOut, int &bestSOut)
 {
     const uint32_t xsB = c.xsB, upB = c.upB;
@@ -154,7 +157,24 @@ __device__ __forceinline__ void match_one(const MatchCtx &c, int si, int cap, in
     uint32_t mLo = 0x00FFFFFFu, mHi = 0u;               // bytes 0..bestL must agree to beat bestL
     // one ascending chain per bucket over the whole region: enter it at the first sub-region the window touches
     int s = (int)lds_u16(c.headB + 2 * (sr0 * MT_HB + h));
-    while (s < lo) s = (int)lds_u16(upB + 2 * s);       // entries before the window (MT_NONE = 0xFFFF ends it)
+    // entries before the window (MT_NONE = 0xFFFF ends the loop).  A bucket that holds most slots (runs of one byte,
+    // short periods) would be stepped through entry by entry, hundreds of dependent loads per position: after a few
+    // dozen steps look whether the window's first slots are in this bucket themselves -- a slot with this hash value IS a
+    // chain entry, and the first of lo, lo + 1, ... that has it is the first entry at or beyond lo.
+    if (DENSE) {
+        for (int trips = 0; s < lo; trips++) {
+            s = (int)lds_u16(upB + 2 * s);              // four entries per trip: the trip counter costs a quarter
+            if (s < lo) s = (int)lds_u16(upB + 2 * s);
+            if (s < lo) s = (int)lds_u16(upB + 2 * s);
+            if (s < lo) s = (int)lds_u16(upB + 2 * s);
+            if (trips == MT_DENSE_TRIPS) {
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (s < lo && lo + t < hi && hash24(lds_u32_unaligned(xsB + lo + t), MT_HBITS) == h) s = lo + t;
+            }
+        }
+    } else
+        while (s < lo) s = (int)lds_u16(upB + 2 * s);
     for (;;) {
         if (s >= hi) break;                             // range exhausted (MT_NONE >= hi as well)
         const int cur = s;
@@ -319,7 +339,7 @@ __device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &c
                 const int lo = max(si - kWindow, ctx.minSlot);
                 const int q = (si - lo + split - 1) >> shift;
                 const int rlo = lo + part * q, rhi = min(si, rlo + q);
-                if (rlo < rhi) match_one(ctx, si, cap, rlo, rhi, bestL, bestS);
+                if (rlo < rhi) match_one<true>(ctx, si, cap, rlo, rhi, bestL, bestS);
             }
             uint32_t key = bestL >= kMinLen ? ((uint32_t)bestL << 13) | (0x1FFFu - (uint32_t)bestS) : 0u;
             for (int d = 1; d < split; d <<= 1) key = max(key, __shfl_xor_sync(0xFFFFFFFFu, key, d));
