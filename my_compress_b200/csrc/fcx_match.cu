@@ -24,10 +24,10 @@
 // busy.  So when a tile has long chains its positions are first counting-sorted by estimated
 // chain length (bucket populations, half-octave bins, heaviest first) and lanes take
 // consecutive entries of that order: neighbouring lanes then walk chains of similar length.
-// Long-match tiles are handled lazily.  A 64-position probe measures the mean match length;
+// Long-match tiles are handled lazily.  A 32-position probe measures the mean match length;
 // when it is large, almost every position lies inside a match of an earlier position and will
 // never be a parse cursor.  The parse can only enter a tile at offsets 0..257, so such a tile
-// evaluates exactly those 258 positions plus a speculative chain start every 32 positions, and
+// evaluates exactly those 258 positions plus a speculative chain start every 128 positions, and
 // follows next(p) = p + len + 1 from each until it lands on a position that is already
 // evaluated (chains merge after a token or two).  The evaluated set then contains every
 // possible entry and is closed under next(), so whatever the true entry turns out to be, the
@@ -49,25 +49,38 @@ constexpr int MT_NSUB = MT_REGION / MT_SUB;      // 6
 #define FCX_MT_HBITS FCX_MT_SUBBITS   // (six sub-regions with 11 bits drop a resident CTA, 9 bits double the collisions: both measured slower)
 #endif
 #ifndef FCX_MT_SPEC_STRIDE
-#define FCX_MT_SPEC_STRIDE 32    // 16/32/64/128 measured on the phrase corpus: 32 best
+#define FCX_MT_SPEC_STRIDE 128   // round 1: 32 best of 16..128; with several lanes per position in the thin rounds (round 2) 128 beats 32..256
 #endif
 constexpr int MT_HBITS = FCX_MT_HBITS;
 constexpr int MT_HB = 1 << MT_HBITS;             // buckets per sub-region
 constexpr int MT_LOOK = 272;                     // >= 257 + 8 + 7: the 8-byte visit window, then lcp_capped's look-ahead
 constexpr int MT_THREADS = 256;
 constexpr int MT_PER_THREAD = MT_TILE / MT_THREADS;   // 16
-constexpr int MT_PROBES = 64;                         // positions sampled per tile
-constexpr int MT_PROBE_CAP = 40;                      // probed matches are not followed beyond this
-constexpr int MT_LONG_MEAN = 12;                      // mean probed match length that switches a tile to lazy evaluation
+#ifndef FCX_MT_PROBES
+#define FCX_MT_PROBES 32
+#endif
+constexpr int MT_PROBES = FCX_MT_PROBES;
+static_assert(MT_PROBES % 32 == 0, "whole warps probe: the sum below is a full-mask shuffle");                         // positions sampled per tile
+#ifndef FCX_MT_PROBE_CAP
+#define FCX_MT_PROBE_CAP 16
+#endif
+constexpr int MT_PROBE_CAP = FCX_MT_PROBE_CAP;                      // probed matches are not followed beyond this
+#ifndef FCX_MT_LONG_MEAN
+#define FCX_MT_LONG_MEAN 12
+#endif
+constexpr int MT_LONG_MEAN = FCX_MT_LONG_MEAN;                      // mean probed match length that switches a tile to lazy evaluation
 #ifndef FCX_MT_LAZY_SPLIT_LOG2
 #define FCX_MT_LAZY_SPLIT_LOG2 3
 #endif
 constexpr int MT_LAZY_SPLIT_LOG2 = FCX_MT_LAZY_SPLIT_LOG2;            // lazy mode: up to 2^this lanes per position in rounds with few positions
-constexpr int MT_SPEC_STRIDE = FCX_MT_SPEC_STRIDE;                    // lazy mode: a speculative chain starts every 32 positions
+constexpr int MT_SPEC_STRIDE = FCX_MT_SPEC_STRIDE;                    // lazy mode: a speculative chain starts every MT_SPEC_STRIDE positions
 constexpr uint32_t MT_NONE = 0xFFFF;
 constexpr int MT_DENSE_TRIPS = 15;                // after 64 skipped entries the window's first slots are tried directly
 constexpr int MT_BINS = 32;
-constexpr uint32_t MT_SORT_THRESHOLD = 12;       // sort only when some bucket holds more than this
+#ifndef FCX_MT_SORT_THRESHOLD
+#define FCX_MT_SORT_THRESHOLD 12
+#endif
+constexpr uint32_t MT_SORT_THRESHOLD = FCX_MT_SORT_THRESHOLD;       // sort only when some bucket holds more than this
 
 struct MatchSmem {
     uint32_t xs[(MT_REGION + MT_LOOK) / 4];
@@ -283,7 +296,7 @@ __device__ __forceinline__ void match_tile_eager(MatchSmem &sm, const MatchCtx &
 }
 
 // lazy mode (long-match tiles): evaluate the 258 possible parse entries and a speculative start
-// every 32 positions, then follow every chain until it lands on an evaluated position
+// every MT_SPEC_STRIDE positions, then follow every chain until it lands on an evaluated position
 __device__ __forceinline__ void match_tile_lazy(MatchSmem &sm, const MatchCtx &ctx, int tileSlots,
                                                 int regionBase, int n, size_t outBase,
                                                 uint8_t *__restrict__ lenCode, uint16_t *__restrict__ dist)
@@ -478,7 +491,7 @@ k_match(const uint8_t *__restrict__ in, const uint32_t *__restrict__ blkLen,
             const int i = regionBase + si;
             const int cap = min(kMaxLen, n - 1 - i);
             if (i > 0 && cap >= kMinLen) {
-                // the probe only has to tell "mean length >= 12" from "short": matches are followed to 40 bytes at
+                // the probe only has to tell "mean length >= 12" from "short": matches are followed to MT_PROBE_CAP bytes at
                 // most (one probe lane walking a 257-byte match kept the other 192 threads at the barrier)
                 int bl = 0, bs = 0;
                 match_one(ctx, si, min(cap, MT_PROBE_CAP), max(si - kWindow, minSlot), si, bl, bs);
