@@ -116,7 +116,7 @@ void fcx_host_free(void *p);
 typedef struct fcx_ctx fcx_ctx;
 
 /* Workspace for batches of up to max_batch_blocks (1..1024) 1 MiB blocks on CUDA device `device`
- * (about 6.7 MiB of HBM per block); longer inputs run as several batches on the same workspace.
+ * (about 4.7 MiB of HBM per block); longer inputs run as several batches on the same workspace.
  * stream: a cudaStream_t (0 = legacy default). */
 int fcx_ctx_create(fcx_ctx **ctx, int device, uint32_t max_batch_blocks);
 void fcx_ctx_destroy(fcx_ctx *ctx);
