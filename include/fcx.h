@@ -181,6 +181,11 @@ int fcx_probe_huffman_section(fcx_ctx *ctx, const uint8_t *d_src, uint32_t S, ui
  * two 256-byte guard bands.  check = 0 paints them; check = 1 returns how many bands were written to since. */
 int fcx_ctx_debug_guards(fcx_ctx *ctx, int check);
 
+/* The host path's pipeline plan for one device (tests): how `blocks` 1 MiB blocks are cut into device batches
+ * (a short first and last batch so that only a small upload / download is exposed, large ones between).
+ * Writes up to cap batch sizes to sizes[] and returns the number of batches. */
+uint32_t fcx_debug_pipeline_plan(uint64_t blocks, uint32_t *sizes, uint32_t cap);
+
 /* Corpus generator following RandM() of the reference's generator program
  * (随机数的生成.cpp:26-42) with time() pinned to `seed`: byte i = perm[i] & 0xFF. */
 void fcx_datagen_randm(uint8_t *out, uint32_t m, uint32_t seed);

@@ -40,7 +40,7 @@ EXPORTS = [
     "fcx_compress_records_lz77", "fcx_decompress_records_lz77", "fcx_host_alloc", "fcx_host_free",
     "fcx_compress_lz77_x9", "fcx_compress_records_lz77_x9", "fcx_compress_block_lz77_x9", "fcx_decompress_block_lz77_x9",
     "fcx_decompress_records_lz77_x9", "fcx_decompress_lz77_device_x9",
-    "fcx_ctx_debug_guards", "fcx_probe_match", "fcx_probe_match_auto", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
+    "fcx_ctx_debug_guards", "fcx_debug_pipeline_plan", "fcx_probe_match", "fcx_probe_match_auto", "fcx_probe_streams", "fcx_probe_huffman_section", "fcx_datagen_randm",
 ]
 
 
@@ -97,6 +97,8 @@ def lib():
                                     C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.fcx_probe_huffman_section.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                             C.POINTER(C.c_uint32)]
+    L.fcx_debug_pipeline_plan.restype = C.c_uint32
+    L.fcx_debug_pipeline_plan.argtypes = [C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32]
     L.fcx_datagen_randm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     L.fcx_datagen_randm.restype = None
     _lib = L

@@ -313,6 +313,13 @@ int compress_host(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, 
 
 } // namespace
 
+extern "C" uint32_t fcx_debug_pipeline_plan(uint64_t blocks, uint32_t *sizes, uint32_t cap)
+{
+    const std::vector<uint32_t> plan = pipeline_plan(blocks);
+    for (size_t i = 0; i < plan.size() && i < cap && sizes; i++) sizes[i] = plan[i];
+    return (uint32_t)plan.size();
+}
+
 extern "C" int fcx_compress_lz77(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t outCap, uint64_t *outN,
                                  uint32_t deviceMask)
 {

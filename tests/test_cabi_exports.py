@@ -87,3 +87,18 @@ def test_randm_generator_is_a_flat_permutation(L):
     assert np.array_equal(np.bincount(b, minlength=256), np.full(256, 256))
     assert np.array_equal(b, api.datagen_randm(1 << 16, 20261018))
     assert not np.array_equal(b, api.datagen_randm(1 << 16, 7))
+
+
+def test_pipeline_plan_covers_every_block_within_the_batch_limits(L):
+    # the host path deals these batches to a device (csrc/fcx_host.cu): every block exactly once, no batch beyond the
+    # 1024-block device limit, never more batches than the per-device event pool (256), short first and last batch
+    sizes = (C.c_uint32 * 512)()
+    for blocks in (0, 1, 2, 15, 16, 17, 40, 255, 256, 257, 511, 512, 513, 1000, 1024, 1025, 4096, 8192, 65535, 200000):
+        k = L.fcx_debug_pipeline_plan(blocks, sizes, 512)
+        plan = [int(sizes[i]) for i in range(min(k, 512))]
+        assert k <= 256 and k == len(plan), (blocks, k)
+        assert sum(plan) == blocks and all(0 < s <= 1024 for s in plan), (blocks, plan[:6], plan[-4:])
+        if blocks >= 512:
+            assert plan[0] == 8 and plan[-1] == 8 and max(plan) >= 128
+        elif blocks > 16:
+            assert plan[0] <= 16 and plan[-1] <= 16
